@@ -1,0 +1,1122 @@
+// ===========================================================================
+// ORACLE -- TEST INFRASTRUCTURE ONLY.
+//
+// CPU restatement of the tracer-advection hot path of E3SM-Project/transport_se
+// (reference mounted at /root/reference; citations below are relative to it).
+// It follows the reference's loop order and operation order so that it can act
+// as the parity checker for the CUDA path.  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load this library;
+// nothing in transport_se_b200/ links or calls it.
+//
+// PARITY PIN: the reference is Fortran + MPI + netCDF and cannot be built in
+// this image (no Fortran compiler).  The oracle is pinned against the
+// reference's own published end-of-run error norms for the shipped
+// configuration (README:94-96 ne8, README:127-129 ne30), against the analytic
+// known answers the reference self-checks (GLL, Dvv(1,1)=-3, sum(spheremp)=4pi,
+// unit-sphere integral), see tests/test_oracle_golden.py.
+//
+// Geometry / edge descriptors are INPUTS here (as they are for the reference's
+// prim_advection_mod): the host-side mesh library hands them over in the
+// reference's own formats (element_t fields, EdgeDescriptor_t put/get maps).
+// ===========================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr int NP = 4;
+constexpr int NPSQ = 16;
+// physical_constants.F90:16-34
+const double DD_PI = 3.141592653589793238462643383279;
+const double rearth = 6.376e6;
+const double rrearth = 1.0 / rearth;
+const double g_grav = 9.80616;
+const double Rgas = 287.04;
+const double p0 = 100000.0;
+
+// direction order of control_mod.F90:173-181 (0-based)
+enum { WEST = 0, EAST = 1, SOUTH = 2, NORTH = 3, SWEST = 4, SEAST = 5, NWEST = 6, NEAST = 7 };
+// DSSopt values, prim_advection_mod.F90:454-457
+enum { DSSeta = 1, DSSomega = 2, DSSdiv_vdp_ave = 3, DSSno_var = -1 };
+
+inline int IX(int i, int j) { return i + NP * j; }  // Fortran (i,j), 0-based
+
+// ---------------------------------------------------------------------------
+// Element operators (derivative_mod.F90)
+// Dvv(i,l) is stored at dvv[i + 4*l]; Dinv(a,b,i,j) at dinv[(i+4j)*4 + a + 2*b].
+// ---------------------------------------------------------------------------
+struct ElemGeo {
+  const double* metdet;
+  const double* rmetdet;
+  const double* spheremp;
+  const double* rspheremp;
+  const double* dinv;
+};
+
+inline double DI(const double* dinv, int a, int b, int i, int j) { return dinv[(i + 4 * j) * 4 + a + 2 * b]; }
+
+// divergence_sphere, derivative_mod.F90:2364-2414
+void divergence_sphere(const double* v, const double* dvv, const ElemGeo& e, double* div) {
+  double gv[2][NPSQ], vvtemp[NPSQ];
+  for (int j = 0; j < NP; ++j)
+    for (int i = 0; i < NP; ++i) {
+      gv[0][IX(i, j)] = e.metdet[IX(i, j)] * (DI(e.dinv, 0, 0, i, j) * v[IX(i, j)] + DI(e.dinv, 0, 1, i, j) * v[16 + IX(i, j)]);
+      gv[1][IX(i, j)] = e.metdet[IX(i, j)] * (DI(e.dinv, 1, 0, i, j) * v[IX(i, j)] + DI(e.dinv, 1, 1, i, j) * v[16 + IX(i, j)]);
+    }
+  for (int j = 0; j < NP; ++j)
+    for (int l = 0; l < NP; ++l) {
+      double dudx00 = 0.0, dvdy00 = 0.0;
+      for (int i = 0; i < NP; ++i) {
+        dudx00 = dudx00 + dvv[i + 4 * l] * gv[0][IX(i, j)];
+        dvdy00 = dvdy00 + dvv[i + 4 * l] * gv[1][IX(j, i)];
+      }
+      div[IX(l, j)] = dudx00;
+      vvtemp[IX(j, l)] = dvdy00;
+    }
+  for (int j = 0; j < NP; ++j)
+    for (int i = 0; i < NP; ++i) div[IX(i, j)] = (div[IX(i, j)] + vvtemp[IX(i, j)]) * (e.rmetdet[IX(i, j)] * rrearth);
+}
+
+// gradient_sphere, derivative_mod.F90:1660-1700
+void gradient_sphere(const double* s, const double* dvv, const double* dinv, double* ds) {
+  double v1[NPSQ], v2[NPSQ];
+  for (int j = 0; j < NP; ++j)
+    for (int l = 0; l < NP; ++l) {
+      double dsdx00 = 0.0, dsdy00 = 0.0;
+      for (int i = 0; i < NP; ++i) {
+        dsdx00 = dsdx00 + dvv[i + 4 * l] * s[IX(i, j)];
+        dsdy00 = dsdy00 + dvv[i + 4 * l] * s[IX(j, i)];
+      }
+      v1[IX(l, j)] = dsdx00 * rrearth;
+      v2[IX(j, l)] = dsdy00 * rrearth;
+    }
+  for (int j = 0; j < NP; ++j)
+    for (int i = 0; i < NP; ++i) {
+      ds[IX(i, j)] = DI(dinv, 0, 0, i, j) * v1[IX(i, j)] + DI(dinv, 1, 0, i, j) * v2[IX(i, j)];
+      ds[16 + IX(i, j)] = DI(dinv, 0, 1, i, j) * v1[IX(i, j)] + DI(dinv, 1, 1, i, j) * v2[IX(i, j)];
+    }
+}
+
+// divergence_sphere_wk, derivative_mod.F90:2027-2097
+void divergence_sphere_wk(const double* v, const double* dvv, const ElemGeo& e, double* div) {
+  double vtemp[2][NPSQ];
+  for (int j = 0; j < NP; ++j)
+    for (int i = 0; i < NP; ++i) {
+      vtemp[0][IX(i, j)] = (DI(e.dinv, 0, 0, i, j) * v[IX(i, j)] + DI(e.dinv, 0, 1, i, j) * v[16 + IX(i, j)]);
+      vtemp[1][IX(i, j)] = (DI(e.dinv, 1, 0, i, j) * v[IX(i, j)] + DI(e.dinv, 1, 1, i, j) * v[16 + IX(i, j)]);
+    }
+  for (int n = 0; n < NP; ++n)
+    for (int m = 0; m < NP; ++m) {
+      double d = 0;
+      for (int j = 0; j < NP; ++j)
+        d = d - (e.spheremp[IX(j, n)] * vtemp[0][IX(j, n)] * dvv[m + 4 * j] +
+                 e.spheremp[IX(m, j)] * vtemp[1][IX(m, j)] * dvv[n + 4 * j]) *
+                    rrearth;
+      div[IX(m, n)] = d;
+    }
+}
+
+// laplace_sphere_wk, derivative_mod.F90:2418-2460 (constant-coefficient branch:
+// hypervis_power = hypervis_scaling = 0, so var_coef is a no-op)
+void laplace_sphere_wk(const double* s, const double* dvv, const ElemGeo& e, double* lap) {
+  double grads[32];
+  gradient_sphere(s, dvv, e.dinv, grads);
+  divergence_sphere_wk(grads, dvv, e, lap);
+}
+
+// ---------------------------------------------------------------------------
+// limiter_optim_iter_full, prim_advection_mod.F90:976-1094
+// ---------------------------------------------------------------------------
+void limiter_optim_iter_full(double* ptens, const double* sphweights, double* minp, double* maxp, const double* dpmass) {
+  const int maxiter = NP * NP - 1;
+  const double tol_limiter = (double)5e-14f;  // default-real literal in the reference (:1003)
+  double x[NPSQ], c[NPSQ];
+  int k1 = 0;
+  for (int i = 0; i < NP; ++i)
+    for (int j = 0; j < NP; ++j) {
+      c[k1] = sphweights[IX(i, j)] * dpmass[IX(i, j)];
+      x[k1] = ptens[IX(i, j)] / dpmass[IX(i, j)];
+      ++k1;
+    }
+  double sumc = 0;
+  for (k1 = 0; k1 < NPSQ; ++k1) sumc += c[k1];
+  if (sumc <= 0) return;
+  double mass = 0;
+  for (k1 = 0; k1 < NPSQ; ++k1) mass += c[k1] * x[k1];
+
+  if (mass < (*minp) * sumc) *minp = mass / sumc;
+  if (mass > (*maxp) * sumc) *maxp = mass / sumc;
+
+  for (int iter = 1; iter <= maxiter; ++iter) {
+    double addmass = 0.0;
+    for (k1 = 0; k1 < NPSQ; ++k1) {
+      if (x[k1] > *maxp) {
+        addmass = addmass + (x[k1] - *maxp) * c[k1];
+        x[k1] = *maxp;
+      }
+      if (x[k1] < *minp) {
+        addmass = addmass - (*minp - x[k1]) * c[k1];
+        x[k1] = *minp;
+      }
+    }
+    if (std::fabs(addmass) <= tol_limiter * std::fabs(mass)) break;
+    double weightssum = 0.0;
+    if (addmass > 0) {
+      for (k1 = 0; k1 < NPSQ; ++k1)
+        if (x[k1] < *maxp) weightssum = weightssum + c[k1];
+      for (k1 = 0; k1 < NPSQ; ++k1)
+        if (x[k1] < *maxp) x[k1] = x[k1] + addmass / weightssum;
+    } else {
+      for (k1 = 0; k1 < NPSQ; ++k1)
+        if (x[k1] > *minp) weightssum = weightssum + c[k1];
+      for (k1 = 0; k1 < NPSQ; ++k1)
+        if (x[k1] > *minp) x[k1] = x[k1] + addmass / weightssum;
+    }
+  }
+  k1 = 0;
+  for (int i = 0; i < NP; ++i)
+    for (int j = 0; j < NP; ++j) {
+      ptens[IX(i, j)] = x[k1];
+      ++k1;
+    }
+  for (int n = 0; n < NPSQ; ++n) ptens[n] = ptens[n] * dpmass[n];
+}
+
+// ---------------------------------------------------------------------------
+// vertremap_mod, prim_advection_mod.F90:98-356 (vert_remap_q_alg /= 2: mirrored BC)
+// ---------------------------------------------------------------------------
+// compute_ppm_grids :221-260.  dx index -1..nlev+2 -> dx[j+1]; rslt(c,j) j=0..nlev+1 -> r[j*10 + c-1]
+void compute_ppm_grids(const double* dxs, int nlev, double* r) {
+  auto dx = [&](int j) { return dxs[j + 1]; };
+  for (int j = 0; j <= nlev + 1; ++j) {
+    r[j * 10 + 0] = dx(j) / (dx(j - 1) + dx(j) + dx(j + 1));
+    r[j * 10 + 1] = (2. * dx(j - 1) + dx(j)) / (dx(j + 1) + dx(j));
+    r[j * 10 + 2] = (dx(j) + 2. * dx(j + 1)) / (dx(j - 1) + dx(j));
+  }
+  for (int j = 0; j <= nlev; ++j) {
+    r[j * 10 + 3] = dx(j) / (dx(j) + dx(j + 1));
+    r[j * 10 + 4] = 1. / (dx(j - 1) + dx(j) + dx(j + 1) + dx(j + 2));  // 1./sum(dx(j-1:j+2))
+    r[j * 10 + 5] = (2. * dx(j + 1) * dx(j)) / (dx(j) + dx(j + 1));
+    r[j * 10 + 6] = (dx(j - 1) + dx(j)) / (2. * dx(j) + dx(j + 1));
+    r[j * 10 + 7] = (dx(j + 2) + dx(j + 1)) / (2. * dx(j + 1) + dx(j));
+    r[j * 10 + 8] = dx(j) * (dx(j - 1) + dx(j)) / (2. * dx(j) + dx(j + 1));
+    r[j * 10 + 9] = dx(j + 1) * (dx(j + 1) + dx(j + 2)) / (dx(j) + 2. * dx(j + 1));
+  }
+}
+
+// compute_ppm :267-342.  a index -1..nlev+2 -> as[j+1]; coefs(0:2, 1..nlev) -> coefs[(j-1)*3 + c]
+void compute_ppm(const double* as, const double* r, int nlev, double* coefs, double* ai, double* dma) {
+  auto a = [&](int j) { return as[j + 1]; };
+  auto dx = [&](int c, int j) { return r[j * 10 + c - 1]; };
+  for (int j = 0; j <= nlev + 1; ++j) {
+    double da = dx(1, j) * (dx(2, j) * (a(j + 1) - a(j)) + dx(3, j) * (a(j) - a(j - 1)));
+    double m = std::min(std::fabs(da), std::min(2. * std::fabs(a(j) - a(j - 1)), 2. * std::fabs(a(j + 1) - a(j))));
+    dma[j] = m * std::copysign(1.0, da);
+    if ((a(j + 1) - a(j)) * (a(j) - a(j - 1)) <= 0.) dma[j] = 0.;
+  }
+  for (int j = 0; j <= nlev; ++j) {
+    ai[j] = a(j) + dx(4, j) * (a(j + 1) - a(j)) +
+            dx(5, j) * (dx(6, j) * (dx(7, j) - dx(8, j)) * (a(j + 1) - a(j)) - dx(9, j) * dma[j + 1] + dx(10, j) * dma[j]);
+  }
+  for (int j = 1; j <= nlev; ++j) {
+    double al = ai[j - 1];
+    double ar = ai[j];
+    if ((ar - a(j)) * (a(j) - al) <= 0.) {
+      al = a(j);
+      ar = a(j);
+    }
+    if ((ar - al) * (a(j) - (al + ar) / 2.) > (ar - al) * (ar - al) / 6.) al = 3. * a(j) - 2. * ar;
+    if ((ar - al) * (a(j) - (al + ar) / 2.) < -((ar - al) * (ar - al)) / 6.) ar = 3. * a(j) - 2. * al;
+    coefs[(j - 1) * 3 + 0] = 1.5 * a(j) - (al + ar) / 4.;
+    coefs[(j - 1) * 3 + 1] = ar - al;
+    coefs[(j - 1) * 3 + 2] = -6. * a(j) + 3. * (al + ar);
+  }
+}
+
+// integrate_parabola :349-356
+inline double integrate_parabola(const double* a, double x1, double x2) {
+  return a[0] * (x2 - x1) + a[1] * (x2 * x2 - x1 * x1) / 0.2e1 + a[2] * (x2 * x2 * x2 - x1 * x1 * x1) / 0.3e1;
+}
+
+// remap_Q_ppm :98-214.  Qdp(nx,nx,nlev,qsize) -> Qdp[((q*nlev + k)*nx + j)*nx + i]
+void remap_Q_ppm(double* Qdp, int nx, int nlev, int qsize, const double* dp1, const double* dp2) {
+  const int gs = 2;
+  std::vector<double> pio(nlev + 2), pin(nlev + 1), masso(nlev + 1), ao(nlev + 2 * gs), dpo(nlev + 2 * gs);
+  std::vector<double> coefs(3 * nlev), z1(nlev), z2(nlev), ppmdx(10 * (nlev + 2)), ai(nlev + 1), dma(nlev + 2);
+  std::vector<int> kid(nlev);
+  const int nn = nx * nx;
+  // arrays with Fortran index 1-gs..nlev+gs are stored at [idx + gs - 1]
+  auto DPO = [&](int k) -> double& { return dpo[k + gs - 1]; };
+  auto AO = [&](int k) -> double& { return ao[k + gs - 1]; };
+  for (int j = 0; j < nx; ++j)
+    for (int i = 0; i < nx; ++i) {
+      const int n = i + nx * j;
+      pin[0] = 0;
+      pio[0] = 0;
+      for (int k = 1; k <= nlev; ++k) {
+        DPO(k) = dp1[(k - 1) * nn + n];
+        pin[k] = pin[k - 1] + dp2[(k - 1) * nn + n];
+        pio[k] = pio[k - 1] + DPO(k);
+      }
+      pio[nlev + 1] = pio[nlev] + 1.;
+      pin[nlev] = pio[nlev];
+      for (int k = 1; k <= gs; ++k) {
+        DPO(1 - k) = DPO(k);
+        DPO(nlev + k) = DPO(nlev + 1 - k);
+      }
+      for (int k = 1; k <= nlev; ++k) {
+        int kk = k;
+        while (pio[kk - 1] <= pin[k]) kk = kk + 1;  // pio(kk) <= pin(k+1), 1-based
+        kk = kk - 1;
+        if (kk == nlev + 1) kk = nlev;
+        kid[k - 1] = kk;
+        z1[k - 1] = -0.5;
+        z2[k - 1] = (pin[k] - (pio[kk - 1] + pio[kk]) * 0.5) / DPO(kk);
+      }
+      compute_ppm_grids(dpo.data(), nlev, ppmdx.data());
+      for (int q = 0; q < qsize; ++q) {
+        double* col = Qdp + (size_t)q * nlev * nn + n;
+        masso[0] = 0.;
+        for (int k = 1; k <= nlev; ++k) {
+          AO(k) = col[(size_t)(k - 1) * nn];
+          masso[k] = masso[k - 1] + AO(k);
+          AO(k) = AO(k) / DPO(k);
+        }
+        for (int k = 1; k <= gs; ++k) {
+          AO(1 - k) = AO(k);
+          AO(nlev + k) = AO(nlev + 1 - k);
+        }
+        compute_ppm(ao.data(), ppmdx.data(), nlev, coefs.data(), ai.data(), dma.data());
+        double massn1 = 0.;
+        for (int k = 1; k <= nlev; ++k) {
+          int kk = kid[k - 1];
+          double massn2 = masso[kk - 1] + integrate_parabola(&coefs[(kk - 1) * 3], z1[k - 1], z2[k - 1]) * DPO(kk);
+          col[(size_t)(k - 1) * nn] = massn2 - massn1;
+          massn1 = massn2;
+        }
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// DCMIP 2012 tests 1-1 and 1-2 point functions, dcmip_123_mod.F90:85-272, :279-409
+// (a = rearth, Rd = Rgas, HOMME constants)
+// ---------------------------------------------------------------------------
+struct Pt {
+  double u, v, w, T, phis, ps, rho, q[4];
+};
+
+void test1_advection_deformation(double time, double lon, double lat, double& p, double z, int zcoords, Pt& o) {
+  const double a = rearth, Rd = Rgas, pi = DD_PI;
+  const double tau = 12.0 * 86400.0, u0 = (2.0 * pi * a) / tau, k0 = (10.0 * a) / tau, omega0 = (23000.0 * pi) / tau, T0 = 300.0,
+               H = Rd * T0 / g_grav, RR = 1.0 / 2.0, ZZ = 1000.0, z0 = 5000.0, lambda0 = 5.0 * pi / 6.0,
+               lambda1 = 7.0 * pi / 6.0, phi0 = 0.0, phi1 = 0.0;
+  double height;
+  if (zcoords == 1) {
+    height = z;
+    p = p0 * std::exp(-z / H);
+  } else {
+    height = H * std::log(p0 / p);
+  }
+  double ptop = p0 * std::exp(-12000.0 / H);
+  double lonp = lon - 2.0 * pi * time / tau;
+  double plim = std::max(p, ptop);
+  double bs = (double)0.2f;  // "bs = 0.2": default-real literal (:161)
+  double s = 1.0 + std::exp((ptop - p0) / (bs * ptop)) - std::exp((plim - p0) / (bs * ptop)) - std::exp((ptop - plim) / (bs * ptop));
+  double cl = std::cos(lat);
+  double ud = (omega0 * a) / (bs * ptop) * std::cos(lonp) * (cl * cl) * std::cos(2.0 * pi * time / tau) *
+              (-std::exp((plim - p0) / (bs * ptop)) + std::exp((ptop - plim) / (bs * ptop)));
+  o.u = k0 * std::sin(lonp) * std::sin(lonp) * std::sin(2.0 * lat) * std::cos(pi * time / tau) + u0 * std::cos(lat) + ud;
+  o.v = k0 * std::sin(2.0 * lonp) * std::cos(lat) * std::cos(pi * time / tau);
+  o.w = -((Rd * T0) / (g_grav * plim)) * omega0 * std::sin(lonp) * std::cos(lat) * std::cos(2.0 * pi * time / tau) * s;
+  o.T = T0;
+  o.phis = 0.0;
+  o.ps = p0;
+  o.rho = p / (Rd * o.T);
+  double sin_tmp = std::sin(lat) * std::sin(phi0), cos_tmp = std::cos(lat) * std::cos(phi0);
+  double sin_tmp2 = std::sin(lat) * std::sin(phi1), cos_tmp2 = std::cos(lat) * std::cos(phi1);
+  double r = std::acos(sin_tmp + cos_tmp * std::cos(lon - lambda0));
+  double r2 = std::acos(sin_tmp2 + cos_tmp2 * std::cos(lon - lambda1));
+  double hz = (height - z0) / ZZ;
+  double d1 = std::min(1.0, (r / RR) * (r / RR) + hz * hz);
+  double d2 = std::min(1.0, (r2 / RR) * (r2 / RR) + hz * hz);
+  double q1 = 0.5 * (1.0 + std::cos(pi * d1)) + 0.5 * (1.0 + std::cos(pi * d2));
+  double q2 = 0.9 - 0.8 * q1 * q1;
+  double q3;
+  if (d1 <= RR) q3 = 1.0;
+  else if (d2 <= RR) q3 = 1.0;
+  else q3 = 0.1;
+  if (height > z0 && std::fabs(lat) < 0.125) q3 = 0.1;
+  double q4 = 1.0 - 0.3 * (q1 + q2 + q3);
+  o.q[0] = q1; o.q[1] = q2; o.q[2] = q3; o.q[3] = q4;
+}
+
+void test1_advection_hadley(double time, double lon, double lat, double& p, double& z, int zcoords, Pt& o) {
+  (void)lon;
+  const double a = rearth, Rd = Rgas, pi = DD_PI;
+  const double tau = 1.0 * 86400.0, u0 = 40.0, w0 = 0.15, T0 = 300.0, H = Rd * T0 / g_grav, K = 5.0, z1 = 2000.0, z2 = 5000.0,
+               z0 = 0.5 * (z1 + z2), ztop = 12000.0;
+  double height;
+  if (zcoords == 1) {
+    height = z;
+    p = p0 * std::exp(-z / H);
+  } else {
+    height = H * std::log(p0 / p);
+    z = height;
+  }
+  o.T = T0;
+  o.phis = 0.0;
+  o.ps = p0;
+  double ptop = p0 * std::exp(-ztop / H);
+  o.rho = std::max(p, ptop) / (Rd * o.T);
+  double rho0 = p0 / (Rd * o.T);
+  o.u = u0 * std::cos(lat);
+  double hstar = std::min(height / ztop, 1.0);
+  o.v = -(rho0 / o.rho) * (a * w0 * pi) / (K * ztop) * std::cos(lat) * std::sin(K * lat) * std::cos(pi * hstar) * std::cos(pi * time / tau);
+  o.w = (rho0 / o.rho) * (w0 / K) * (-2.0 * std::sin(K * lat) * std::sin(lat) + K * std::cos(lat) * std::cos(K * lat)) *
+        std::sin(pi * hstar) * std::cos(pi * time / tau);
+  o.q[0] = 0.0;  // q
+  if (height < z2 && height > z1) o.q[1] = 0.5 * (1.0 + std::cos(2.0 * pi * (height - z0) / (z2 - z1)));
+  else o.q[1] = 0.0;
+  o.q[2] = o.q[3] = 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// State (element_mod.F90:20-78), flattened element-major, Fortran index order
+// inside an element: (i,j) fastest.
+// ---------------------------------------------------------------------------
+struct TimeLevel {  // time_mod.F90:25-31,53-60 (1-based level indices)
+  int nm1 = 1, n0 = 2, np1 = 3, nstep = 0;
+};
+
+struct Oracle {
+  int nelem, qsize, nlev, nlevp;
+  int rsplit = 3, qsplit = 1, limiter_option = 8;
+  double nu_q = 0;
+  double ps0 = p0;
+  int test_case = 11;
+  // geometry
+  std::vector<double> dvv, spheremp, rspheremp, metdet, rmetdet, dinv, lat, lon;
+  // edge descriptors + buffer (edge_mod.F90:31-55)
+  std::vector<int> putmap, getmap, reverse;
+  int nbuf = 0;
+  std::vector<double> buf;  // buf(nlyr, nbuf), layer fastest
+  int nlyr = 0;
+  // vertical coordinate (hybvcoord_mod.F90:18-30)
+  std::vector<double> hyai, hybi, hyam, hybm, etam, etai;
+  // state
+  std::vector<double> v;     // [e][tl3][k][c][16]
+  std::vector<double> dp3d;  // [e][tl3][k][16]
+  std::vector<double> ps_v;  // [e][tl3][16]
+  std::vector<double> Q;     // [e][q][k][16]
+  std::vector<double> Qdp;   // [e][tl2][q][k][16]
+  // derived
+  std::vector<double> vn0;  // [e][k][c][16]
+  std::vector<double> dp, divdp, divdp_proj, omega_p, phi;  // [e][k][16]
+  std::vector<double> eta_dot_dpdn;                         // [e][nlevp][16]
+  std::vector<double> qmin, qmax;                           // [e][q][k]  (Fortran qmin(nlev,qsize,nelemd))
+  TimeLevel tl;
+
+  ElemGeo geo(int e) const {
+    return ElemGeo{&metdet[(size_t)e * 16], &rmetdet[(size_t)e * 16], &spheremp[(size_t)e * 16], &rspheremp[(size_t)e * 16],
+                   &dinv[(size_t)e * 64]};
+  }
+  double* qdp(int e, int tlq, int q, int k) { return &Qdp[((((size_t)e * 2 + (tlq - 1)) * qsize + q) * nlev + k) * 16]; }
+  double* vel(int e, int t, int k, int c) { return &v[((((size_t)e * 3 + (t - 1)) * nlev + k) * 2 + c) * 16]; }
+  double* dp3(int e, int t, int k) { return &dp3d[(((size_t)e * 3 + (t - 1)) * nlev + k) * 16]; }
+  double* psv(int e, int t) { return &ps_v[((size_t)e * 3 + (t - 1)) * 16]; }
+  double* lev(std::vector<double>& f, int e, int k) { return &f[((size_t)e * nlev + k) * 16]; }
+};
+
+// TimeLevel_Qdp, time_mod.F90:85-109
+void TimeLevel_Qdp(const TimeLevel& tl, int qsplit, int& n0, int& np1) {
+  int i_temp = tl.nstep / qsplit;
+  if (i_temp % 2 == 0) { n0 = 1; np1 = 2; }
+  else { n0 = 2; np1 = 1; }
+}
+// TimeLevel_update('leapfrog'), time_mod.F90:111-140
+void TimeLevel_update(TimeLevel& tl) {
+  int ntmp = tl.np1;
+  tl.np1 = tl.nm1;
+  tl.nm1 = tl.n0;
+  tl.n0 = ntmp;
+  tl.nstep = tl.nstep + 1;
+}
+
+// ---------------------------------------------------------------------------
+// Edge buffer pack / unpack (edge_mod.F90:366-511, 648-742, 965-1092).
+// v points at vlyr planes of 16.  Offsets are 0-based: slot index = map + t.
+// ---------------------------------------------------------------------------
+inline double& BUF(Oracle& o, int layer, int slot) { return o.buf[(size_t)slot * o.nlyr + layer]; }
+
+void edgeVpack(Oracle& o, const double* v, int vlyr, int kptr, int e) {
+  const int* pm = &o.putmap[e * 8];
+  const int* rv = &o.reverse[e * 8];
+  const int is = pm[SOUTH], ie = pm[EAST], in = pm[NORTH], iw = pm[WEST];
+  for (int k = 0; k < vlyr; ++k) {
+    const int kk = kptr + k;
+    const double* p = v + (size_t)k * 16;
+    for (int i = 0; i < NP; ++i) {
+      BUF(o, kk, is + i) = p[IX(i, 0)];
+      BUF(o, kk, ie + i) = p[IX(NP - 1, i)];
+      BUF(o, kk, in + i) = p[IX(i, NP - 1)];
+      BUF(o, kk, iw + i) = p[IX(0, i)];
+    }
+    if (rv[SOUTH]) for (int i = 0; i < NP; ++i) BUF(o, kk, is + NP - 1 - i) = p[IX(i, 0)];
+    if (rv[EAST]) for (int i = 0; i < NP; ++i) BUF(o, kk, ie + NP - 1 - i) = p[IX(NP - 1, i)];
+    if (rv[NORTH]) for (int i = 0; i < NP; ++i) BUF(o, kk, in + NP - 1 - i) = p[IX(i, NP - 1)];
+    if (rv[WEST]) for (int i = 0; i < NP; ++i) BUF(o, kk, iw + NP - 1 - i) = p[IX(0, i)];
+    if (pm[SWEST] != -1) BUF(o, kk, pm[SWEST]) = p[IX(0, 0)];
+    if (pm[SEAST] != -1) BUF(o, kk, pm[SEAST]) = p[IX(NP - 1, 0)];
+    if (pm[NEAST] != -1) BUF(o, kk, pm[NEAST]) = p[IX(NP - 1, NP - 1)];
+    if (pm[NWEST] != -1) BUF(o, kk, pm[NWEST]) = p[IX(0, NP - 1)];
+  }
+}
+
+template <class OP>
+void edgeVunpack_op(Oracle& o, double* v, int vlyr, int kptr, int e, OP op) {
+  const int* gm = &o.getmap[e * 8];
+  const int is = gm[SOUTH], ie = gm[EAST], in = gm[NORTH], iw = gm[WEST];
+  for (int k = 0; k < vlyr; ++k) {
+    const int kk = kptr + k;
+    double* p = v + (size_t)k * 16;
+    // np=4 unrolled branch (:678-702): all South, then East, North, West
+    for (int i = 0; i < NP; ++i) p[IX(i, 0)] = op(p[IX(i, 0)], BUF(o, kk, is + i));
+    for (int i = 0; i < NP; ++i) p[IX(NP - 1, i)] = op(p[IX(NP - 1, i)], BUF(o, kk, ie + i));
+    for (int i = 0; i < NP; ++i) p[IX(i, NP - 1)] = op(p[IX(i, NP - 1)], BUF(o, kk, in + i));
+    for (int i = 0; i < NP; ++i) p[IX(0, i)] = op(p[IX(0, i)], BUF(o, kk, iw + i));
+    if (gm[SWEST] != -1) p[IX(0, 0)] = op(p[IX(0, 0)], BUF(o, kk, gm[SWEST]));
+    if (gm[SEAST] != -1) p[IX(NP - 1, 0)] = op(p[IX(NP - 1, 0)], BUF(o, kk, gm[SEAST]));
+    if (gm[NEAST] != -1) p[IX(NP - 1, NP - 1)] = op(p[IX(NP - 1, NP - 1)], BUF(o, kk, gm[NEAST]));
+    if (gm[NWEST] != -1) p[IX(0, NP - 1)] = op(p[IX(0, NP - 1)], BUF(o, kk, gm[NWEST]));
+  }
+}
+void edgeVunpack(Oracle& o, double* v, int vlyr, int kptr, int e) {
+  edgeVunpack_op(o, v, vlyr, kptr, e, [](double a, double b) { return a + b; });
+}
+void edgeVunpackMIN(Oracle& o, double* v, int vlyr, int kptr, int e) {
+  edgeVunpack_op(o, v, vlyr, kptr, e, [](double a, double b) { return std::min(a, b); });
+}
+void edgeVunpackMAX(Oracle& o, double* v, int vlyr, int kptr, int e) {
+  edgeVunpack_op(o, v, vlyr, kptr, e, [](double a, double b) { return std::max(a, b); });
+}
+void ensure_buf(Oracle& o, int nlyr) {
+  // initEdgeBuffer (edge_mod.F90:111-259); one rank: bndry_exchangeV moves nothing
+  // because intra-rank put/get slots coincide (schedule_mod.F90:150-151).
+  o.nlyr = nlyr;
+  size_t need = (size_t)nlyr * o.nbuf;
+  if (o.buf.size() < need) o.buf.resize(need);
+}
+
+// ---------------------------------------------------------------------------
+// neighbor_minmax, viscosity_mod.F90:748-816
+// ---------------------------------------------------------------------------
+void neighbor_minmax(Oracle& o) {
+  const int nl = o.nlev * o.qsize;
+  ensure_buf(o, 2 * nl);
+#pragma omp parallel
+  {
+    std::vector<double> Qmin((size_t)nl * 16), Qmax((size_t)nl * 16);
+#pragma omp for schedule(static)
+    for (int e = 0; e < o.nelem; ++e) {
+      for (int l = 0; l < nl; ++l)
+        for (int n = 0; n < 16; ++n) {
+          Qmin[(size_t)l * 16 + n] = o.qmin[(size_t)e * nl + l];
+          Qmax[(size_t)l * 16 + n] = o.qmax[(size_t)e * nl + l];
+        }
+      edgeVpack(o, Qmin.data(), nl, 0, e);
+      edgeVpack(o, Qmax.data(), nl, nl, e);
+    }
+#pragma omp for schedule(static)
+    for (int e = 0; e < o.nelem; ++e) {
+      for (int l = 0; l < nl; ++l)
+        for (int n = 0; n < 16; ++n) {
+          Qmin[(size_t)l * 16 + n] = o.qmin[(size_t)e * nl + l];
+          Qmax[(size_t)l * 16 + n] = o.qmax[(size_t)e * nl + l];
+        }
+      edgeVunpackMIN(o, Qmin.data(), nl, 0, e);
+      edgeVunpackMAX(o, Qmax.data(), nl, nl, e);
+      for (int l = 0; l < nl; ++l) {
+        const double* a = &Qmin[(size_t)l * 16];
+        const double* b = &Qmax[(size_t)l * 16];
+        o.qmin[(size_t)e * nl + l] = std::min(std::min(a[IX(0, 0)], a[IX(0, 3)]), std::min(a[IX(3, 0)], a[IX(3, 3)]));
+        o.qmax[(size_t)e * nl + l] = std::max(std::max(b[IX(0, 0)], b[IX(0, 3)]), std::max(b[IX(3, 0)], b[IX(3, 3)]));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// biharmonic_wk_scalar_minmax, viscosity_mod.F90:353-442
+// qtens: [e][q][k][16] in/out; emin/emax = o.qmin/o.qmax
+// ---------------------------------------------------------------------------
+void biharmonic_wk_scalar_minmax(Oracle& o, std::vector<double>& qtens) {
+  const int nl = o.nlev * o.qsize;
+  ensure_buf(o, 3 * nl);
+#pragma omp parallel
+  {
+    std::vector<double> Qmin((size_t)nl * 16), Qmax((size_t)nl * 16);
+#pragma omp for schedule(static)
+    for (int e = 0; e < o.nelem; ++e) {
+      ElemGeo ge = o.geo(e);
+      double* qt = &qtens[(size_t)e * nl * 16];
+      for (int l = 0; l < nl; ++l) {
+        for (int n = 0; n < 16; ++n) {
+          Qmin[(size_t)l * 16 + n] = o.qmin[(size_t)e * nl + l];
+          Qmax[(size_t)l * 16 + n] = o.qmax[(size_t)e * nl + l];
+        }
+        double lap_p[16], out[16];
+        std::memcpy(lap_p, qt + (size_t)l * 16, sizeof lap_p);
+        laplace_sphere_wk(lap_p, o.dvv.data(), ge, out);
+        std::memcpy(qt + (size_t)l * 16, out, sizeof out);
+      }
+      edgeVpack(o, qt, nl, 0, e);
+      edgeVpack(o, Qmin.data(), nl, nl, e);
+      edgeVpack(o, Qmax.data(), nl, 2 * nl, e);
+    }
+#pragma omp for schedule(static)
+    for (int e = 0; e < o.nelem; ++e) {
+      ElemGeo ge = o.geo(e);
+      double* qt = &qtens[(size_t)e * nl * 16];
+      for (int l = 0; l < nl; ++l)
+        for (int n = 0; n < 16; ++n) {
+          Qmin[(size_t)l * 16 + n] = o.qmin[(size_t)e * nl + l];
+          Qmax[(size_t)l * 16 + n] = o.qmax[(size_t)e * nl + l];
+        }
+      edgeVunpack(o, qt, nl, 0, e);
+      edgeVunpackMIN(o, Qmin.data(), nl, nl, e);
+      edgeVunpackMAX(o, Qmax.data(), nl, 2 * nl, e);
+      for (int l = 0; l < nl; ++l) {
+        double lap_p[16], out[16];
+        for (int n = 0; n < 16; ++n) lap_p[n] = ge.rspheremp[n] * qt[(size_t)l * 16 + n];
+        laplace_sphere_wk(lap_p, o.dvv.data(), ge, out);
+        std::memcpy(qt + (size_t)l * 16, out, sizeof out);
+        const double* a = &Qmin[(size_t)l * 16];
+        const double* b = &Qmax[(size_t)l * 16];
+        o.qmin[(size_t)e * nl + l] = std::min(std::min(a[IX(0, 0)], a[IX(0, 3)]), std::min(a[IX(3, 0)], a[IX(3, 3)]));
+        o.qmax[(size_t)e * nl + l] = std::max(std::max(b[IX(0, 0)], b[IX(0, 3)]), std::max(b[IX(3, 0)], b[IX(3, 3)]));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// euler_step, prim_advection_mod.F90:667-970
+// ---------------------------------------------------------------------------
+double* dss_var(Oracle& o, int DSSopt, int e) {
+  if (DSSopt == DSSeta) return &o.eta_dot_dpdn[(size_t)e * o.nlevp * 16];
+  if (DSSopt == DSSomega) return &o.omega_p[(size_t)e * o.nlev * 16];
+  if (DSSopt == DSSdiv_vdp_ave) return &o.divdp_proj[(size_t)e * o.nlev * 16];
+  return nullptr;
+}
+
+void euler_step(Oracle& o, int np1_qdp, int n0_qdp, double dt, int DSSopt, int rhs_multiplier) {
+  const int nlev = o.nlev, qsize = o.qsize, nl = nlev * qsize;
+  std::vector<double> Qtens_biharmonic((size_t)o.nelem * nl * 16);
+  int rhs_viss = 0;
+
+  // :750-761
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < o.nelem; ++e)
+    for (int k = 0; k < nlev; ++k) {
+      double dp[16];
+      for (int n = 0; n < 16; ++n) dp[n] = o.lev(o.dp, e, k)[n] - rhs_multiplier * dt * o.lev(o.divdp_proj, e, k)[n];
+      for (int q = 0; q < qsize; ++q)
+        for (int n = 0; n < 16; ++n)
+          Qtens_biharmonic[(((size_t)e * qsize + q) * nlev + k) * 16 + n] = o.qdp(e, n0_qdp, q, k)[n] / dp[n];
+    }
+  auto local_minmax = [&](bool accumulate) {
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < o.nelem; ++e)
+      for (int q = 0; q < qsize; ++q)
+        for (int k = 0; k < nlev; ++k) {
+          const double* Qp = &Qtens_biharmonic[(((size_t)e * qsize + q) * nlev + k) * 16];
+          double mn = Qp[0], mx = Qp[0];
+          for (int n = 1; n < 16; ++n) {
+            mn = std::min(mn, Qp[n]);
+            mx = std::max(mx, Qp[n]);
+          }
+          double& qmn = o.qmin[((size_t)e * qsize + q) * nlev + k];
+          double& qmx = o.qmax[((size_t)e * qsize + q) * nlev + k];
+          if (accumulate) {
+            qmn = std::min(qmn, mn);
+            qmx = std::max(qmx, mx);
+          } else {
+            qmn = mn;
+            qmx = mx;
+          }
+        }
+  };
+  if (rhs_multiplier == 0) {  // :764-778
+    local_minmax(false);
+    neighbor_minmax(o);
+  }
+  if (rhs_multiplier == 1) local_minmax(true);  // :781-793
+  if (rhs_multiplier == 2) {                    // :796-827
+    rhs_viss = 3;
+    local_minmax(false);
+    biharmonic_wk_scalar_minmax(o, Qtens_biharmonic);
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < o.nelem; ++e)
+      for (int k = 0; k < nlev; ++k) {
+        double dp0 = (o.hyai[k + 1] - o.hyai[k]) * o.ps0 + (o.hybi[k + 1] - o.hybi[k]) * o.ps0;
+        for (int q = 0; q < qsize; ++q) {
+          double* qb = &Qtens_biharmonic[(((size_t)e * qsize + q) * nlev + k) * 16];
+          for (int n = 0; n < 16; ++n) qb[n] = -rhs_viss * dt * o.nu_q * dp0 * qb[n] / o.spheremp[(size_t)e * 16 + n];
+        }
+      }
+  }
+
+  // 2D advection step :834-921
+  const int nlyr = (DSSopt == DSSno_var) ? nl : nl + nlev;
+  ensure_buf(o, nlyr);
+#pragma omp parallel
+  {
+    std::vector<double> Vstar((size_t)nlev * 32), dp((size_t)nlev * 16), dp_star((size_t)nlev * 16);
+#pragma omp for schedule(static)
+    for (int e = 0; e < o.nelem; ++e) {
+      ElemGeo ge = o.geo(e);
+      double* DSSvar = dss_var(o, DSSopt, e);
+      for (int k = 0; k < nlev; ++k)
+        for (int n = 0; n < 16; ++n) {
+          dp[k * 16 + n] = o.lev(o.dp, e, k)[n] - rhs_multiplier * dt * o.lev(o.divdp_proj, e, k)[n];
+          Vstar[k * 32 + n] = o.vn0[(((size_t)e * nlev + k) * 2 + 0) * 16 + n] / dp[k * 16 + n];
+          Vstar[k * 32 + 16 + n] = o.vn0[(((size_t)e * nlev + k) * 2 + 1) * 16 + n] / dp[k * 16 + n];
+        }
+      if (o.limiter_option == 8)
+        for (int k = 0; k < nlev; ++k)
+          for (int n = 0; n < 16; ++n) dp_star[k * 16 + n] = dp[k * 16 + n] - dt * o.lev(o.divdp, e, k)[n];
+      for (int q = 0; q < qsize; ++q)
+        for (int k = 0; k < nlev; ++k) {
+          double gradQ[32], Qtens[16];
+          const double* q0 = o.qdp(e, n0_qdp, q, k);
+          for (int n = 0; n < 16; ++n) {
+            gradQ[n] = Vstar[k * 32 + n] * q0[n];
+            gradQ[16 + n] = Vstar[k * 32 + 16 + n] * q0[n];
+          }
+          divergence_sphere(gradQ, o.dvv.data(), ge, Qtens);
+          for (int n = 0; n < 16; ++n) Qtens[n] = q0[n] - dt * Qtens[n];
+          if (rhs_viss != 0) {
+            const double* qb = &Qtens_biharmonic[(((size_t)e * qsize + q) * nlev + k) * 16];
+            for (int n = 0; n < 16; ++n) Qtens[n] = Qtens[n] + qb[n];
+          }
+          if (o.limiter_option == 8)
+            limiter_optim_iter_full(Qtens, ge.spheremp, &o.qmin[((size_t)e * qsize + q) * nlev + k],
+                                    &o.qmax[((size_t)e * qsize + q) * nlev + k], &dp_star[k * 16]);
+          double* q1 = o.qdp(e, np1_qdp, q, k);
+          for (int n = 0; n < 16; ++n) q1[n] = ge.spheremp[n] * Qtens[n];
+        }
+      edgeVpack(o, o.qdp(e, np1_qdp, 0, 0), nl, 0, e);
+      if (DSSopt != DSSno_var) {
+        for (int k = 0; k < nlev; ++k)
+          for (int n = 0; n < 16; ++n) DSSvar[k * 16 + n] = ge.spheremp[n] * DSSvar[k * 16 + n];
+        edgeVpack(o, DSSvar, nlev, nl, e);
+      }
+    }
+    // bndry_exchangeV :923-927 -- single rank: nothing moves
+#pragma omp for schedule(static)
+    for (int e = 0; e < o.nelem; ++e) {
+      ElemGeo ge = o.geo(e);
+      double* DSSvar = dss_var(o, DSSopt, e);
+      edgeVunpack(o, o.qdp(e, np1_qdp, 0, 0), nl, 0, e);
+      for (int q = 0; q < qsize; ++q)
+        for (int k = 0; k < nlev; ++k) {
+          double* q1 = o.qdp(e, np1_qdp, q, k);
+          for (int n = 0; n < 16; ++n) q1[n] = ge.rspheremp[n] * q1[n];
+        }
+      if (DSSopt != DSSno_var) {
+        edgeVunpack(o, DSSvar, nlev, nl, e);
+        for (int k = 0; k < nlev; ++k)
+          for (int n = 0; n < 16; ++n) DSSvar[k * 16 + n] = DSSvar[k * 16 + n] * ge.rspheremp[n];
+      }
+    }
+  }
+}
+
+// qdp_time_avg, prim_advection_mod.F90:645-662
+void qdp_time_avg(Oracle& o, int rkstage, int n0_qdp, int np1_qdp) {
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < o.nelem; ++e) {
+    double* a = o.qdp(e, np1_qdp, 0, 0);
+    const double* b = o.qdp(e, n0_qdp, 0, 0);
+    size_t cnt = (size_t)o.qsize * o.nlev * 16;
+    for (size_t i = 0; i < cnt; ++i) a[i] = (b[i] + (rkstage - 1) * a[i]) / rkstage;
+  }
+}
+
+// the divdp precompute of Prim_Advec_Tracers_remap_rk2, :614-623
+void precompute_divdp(Oracle& o) {
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < o.nelem; ++e) {
+    ElemGeo ge = o.geo(e);
+    for (int k = 0; k < o.nlev; ++k) {
+      double* d = o.lev(o.divdp, e, k);
+      divergence_sphere(&o.vn0[((size_t)e * o.nlev + k) * 32], o.dvv.data(), ge, d);
+      std::memcpy(o.lev(o.divdp_proj, e, k), d, 16 * sizeof(double));
+    }
+  }
+}
+
+// Prim_Advec_Tracers_remap_rk2, prim_advection_mod.F90:579-640
+void advec_tracers_remap_rk2(Oracle& o, double dt) {
+  int n0_qdp, np1_qdp;
+  TimeLevel_Qdp(o.tl, o.qsplit, n0_qdp, np1_qdp);
+  const int rkstage = 3;
+  precompute_divdp(o);
+  euler_step(o, np1_qdp, n0_qdp, dt / 2, DSSdiv_vdp_ave, 0);
+  euler_step(o, np1_qdp, np1_qdp, dt / 2, DSSeta, 1);
+  euler_step(o, np1_qdp, np1_qdp, dt / 2, DSSomega, 2);
+  qdp_time_avg(o, rkstage, n0_qdp, np1_qdp);
+}
+
+// vertical_remap, prim_advection_mod.F90:1242-1330.  Returns nonzero on negative thickness.
+int vertical_remap(Oracle& o, double dt, int np1, int np1_qdp) {
+  int bad = 0;
+  const int nlev = o.nlev;
+#pragma omp parallel
+  {
+    std::vector<double> dp((size_t)nlev * 16), dp_star((size_t)nlev * 16);
+#pragma omp for schedule(static)
+    for (int e = 0; e < o.nelem; ++e) {
+      for (int k = 0; k < nlev; ++k)
+        for (int n = 0; n < 16; ++n) o.dp3(e, np1, k)[n] = o.lev(o.dp, e, k)[n] - dt * o.lev(o.divdp_proj, e, k)[n];
+      double* ps = o.psv(e, np1);
+      for (int n = 0; n < 16; ++n) {
+        double s = 0;
+        for (int k = 0; k < nlev; ++k) s += o.dp3(e, np1, k)[n];  // sum(dp3d,3)
+        ps[n] = o.hyai[0] * o.ps0 + s;
+      }
+      double mn = 1e300;
+      for (int k = 0; k < nlev; ++k)
+        for (int n = 0; n < 16; ++n) {
+          dp[k * 16 + n] = (o.hyai[k + 1] - o.hyai[k]) * o.ps0 + (o.hybi[k + 1] - o.hybi[k]) * ps[n];
+          dp_star[k * 16 + n] = o.dp3(e, np1, k)[n];
+          mn = std::min(mn, dp_star[k * 16 + n]);
+        }
+      if (mn < 0) {
+#pragma omp atomic write
+        bad = 1;
+      }
+      remap_Q_ppm(o.qdp(e, np1_qdp, 0, 0), NP, nlev, o.qsize, dp_star.data(), dp.data());
+    }
+  }
+  return bad;
+}
+
+// ---------------------------------------------------------------------------
+// DCMIP wrapper, dcmip_wrapper_mod.F90:49-266
+// ---------------------------------------------------------------------------
+void set_dcmip_fields(Oracle& o, int test, int tlv, double time) {
+  const double T0 = 300.0, H = Rgas * T0 / g_grav;
+  const int nlev = o.nlev, nlevp = o.nlevp, qsize = o.qsize;
+  const int zcoords = 1;
+#pragma omp parallel
+  {
+    std::vector<double> v_m((size_t)nlev * 32), q_m((size_t)nlev * 4 * 16), p_i((size_t)nlevp * 16), z_m((size_t)nlev * 16),
+        eta_dot((size_t)nlevp * 16);
+#pragma omp for schedule(static)
+    for (int e = 0; e < o.nelem; ++e) {
+      for (int k = 0; k < nlev; ++k) {
+        double z = H * std::log(1.0 / o.etam[k]);
+        for (int n = 0; n < 16; ++n) {
+          double p = p0 * o.etam[k];
+          double zz = z;
+          Pt pt;
+          if (test == 11) test1_advection_deformation(time, o.lon[(size_t)e * 16 + n], o.lat[(size_t)e * 16 + n], p, zz, zcoords, pt);
+          else test1_advection_hadley(time, o.lon[(size_t)e * 16 + n], o.lat[(size_t)e * 16 + n], p, zz, zcoords, pt);
+          v_m[k * 32 + n] = pt.u;
+          v_m[k * 32 + 16 + n] = pt.v;
+          for (int c = 0; c < 4; ++c) q_m[((size_t)k * 4 + c) * 16 + n] = pt.q[c];
+          z_m[k * 16 + n] = zz;
+        }
+      }
+      for (int k = 0; k < nlevp; ++k) {
+        double z = H * std::log(1.0 / o.etai[k]);
+        for (int n = 0; n < 16; ++n) {
+          double p = 0;  // reference reads etam(nlevp) out of bounds here; overwritten since zcoords=1
+          double zz = z;
+          Pt pt;
+          if (test == 11) test1_advection_deformation(time, o.lon[(size_t)e * 16 + n], o.lat[(size_t)e * 16 + n], p, zz, zcoords, pt);
+          else test1_advection_hadley(time, o.lon[(size_t)e * 16 + n], o.lat[(size_t)e * 16 + n], p, zz, zcoords, pt);
+          p_i[k * 16 + n] = p;
+          eta_dot[k * 16 + n] = -g_grav * pt.rho * pt.w;
+        }
+      }
+      // set_element_state :162-212
+      for (int k = 0; k < nlev; ++k)
+        for (int n = 0; n < 16; ++n) {
+          double dpk = p_i[(k + 1) * 16 + n] - p_i[k * 16 + n];
+          o.vel(e, tlv, k, 0)[n] = v_m[k * 32 + n];
+          o.vel(e, tlv, k, 1)[n] = v_m[k * 32 + 16 + n];
+          o.dp3(e, tlv, k)[n] = dpk;
+          o.lev(o.dp, e, k)[n] = dpk;
+          o.lev(o.phi, e, k)[n] = z_m[k * 16 + n] * g_grav;
+          o.lev(o.omega_p, e, k)[n] = 0.0;  // reference: built from uninitialised rho,w (:246-255); not parity-checked
+        }
+      for (int n = 0; n < 16; ++n) o.psv(e, tlv)[n] = p_i[(nlevp - 1) * 16 + n];
+      std::memcpy(&o.eta_dot_dpdn[(size_t)e * nlevp * 16], eta_dot.data(), (size_t)nlevp * 16 * sizeof(double));
+      if (time == 0.0) {
+        for (int q = 0; q < qsize; ++q)
+          for (int k = 0; k < nlev; ++k)
+            for (int n = 0; n < 16; ++n) {
+              double qv = q < 4 ? q_m[((size_t)k * 4 + q) * 16 + n] : 0.0;  // q(5:) uninitialised in the reference, overwritten below
+              o.Q[(((size_t)e * qsize + q) * nlev + k) * 16 + n] = qv;
+              o.qdp(e, 1, q, k)[n] = qv * o.dp3(e, tlv, k)[n];
+              o.qdp(e, 2, q, k)[n] = qv * o.dp3(e, tlv, k)[n];
+            }
+        // set_extra_tracers :215-243 (0-based tracer ranges)
+        auto extra = [&](int q1, int q2) {
+          for (int q = q1; q <= q2; ++q)
+            for (int n = 0; n < 16; ++n) {
+              double term = std::sin(9. * o.lon[(size_t)e * 16 + n]) * std::sin(9. * o.lat[(size_t)e * 16 + n]);
+              double val = term < 0. ? 0 : 1;
+              for (int k = 0; k < nlev; ++k) {
+                o.Q[(((size_t)e * qsize + q) * nlev + k) * 16 + n] = val;
+                o.qdp(e, 1, q, k)[n] = val * o.dp3(e, tlv, k)[n];
+                o.qdp(e, 2, q, k)[n] = val * o.dp3(e, tlv, k)[n];
+              }
+            }
+        };
+        if (test == 11) extra(4, qsize - 1);
+        else {
+          extra(0, 0);
+          extra(2, qsize - 1);
+        }
+      }
+    }
+  }
+}
+
+// the part of prim_init2 on the path, prim_driver_mod.F90:551-558, 646-669
+void prim_init2(Oracle& o, int test) {
+  o.test_case = test;
+  o.tl = TimeLevel();
+  set_dcmip_fields(o, test, o.tl.n0, 0.0);
+  std::fill(o.omega_p.begin(), o.omega_p.end(), 0.0);
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < o.nelem; ++e)
+    for (int k = 0; k < o.nlev; ++k)
+      for (int q = 0; q < o.qsize; ++q)
+        for (int n = 0; n < 16; ++n) {
+          double dp = (o.hyai[k + 1] - o.hyai[k]) * o.ps0 + (o.hybi[k + 1] - o.hybi[k]) * o.psv(e, o.tl.n0)[n];
+          double qv = o.Q[(((size_t)e * o.qsize + q) * o.nlev + k) * 16 + n];
+          o.qdp(e, 1, q, k)[n] = qv * dp;
+          o.qdp(e, 2, q, k)[n] = qv * dp;
+        }
+}
+
+// prim_advance_exp, prim_advance_mod.F90:70-152 (qsplit=1: ur_weights(1)=1)
+void prim_advance_exp(Oracle& o, double dt) {
+  double time = o.tl.nstep * dt;
+  set_dcmip_fields(o, o.test_case, o.tl.np1, time);
+  double eta_ave_w = 1.0 / o.qsplit;  // ur_weights for odd qsplit stage 1 (:57-61); qsplit=1 -> 1
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < o.nelem; ++e)
+    for (int k = 0; k < o.nlev; ++k)
+      for (int c = 0; c < 2; ++c)
+        for (int n = 0; n < 16; ++n) {
+          double& vn = o.vn0[(((size_t)e * o.nlev + k) * 2 + c) * 16 + n];
+          vn = vn + eta_ave_w * o.vel(e, o.tl.n0, k, c)[n] * o.lev(o.dp, e, k)[n];
+        }
+}
+
+// prim_step, prim_driver_mod.F90:858-943
+void prim_step(Oracle& o, double dt) {
+  std::fill(o.eta_dot_dpdn.begin(), o.eta_dot_dpdn.end(), 0.0);
+  std::fill(o.vn0.begin(), o.vn0.end(), 0.0);
+  std::fill(o.omega_p.begin(), o.omega_p.end(), 0.0);
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < o.nelem; ++e)
+    for (int k = 0; k < o.nlev; ++k)
+      std::memcpy(o.lev(o.dp, e, k), o.dp3(e, o.tl.n0, k), 16 * sizeof(double));
+  prim_advance_exp(o, dt);
+  advec_tracers_remap_rk2(o, dt * o.qsplit);
+}
+
+// prim_run_subcycle, prim_driver_mod.F90:701-854 (diagnostics omitted)
+int prim_run_subcycle(Oracle& o, double dt) {
+  double dt_q = dt * o.qsplit;
+  double dt_remap = dt_q * o.rsplit;
+  prim_step(o, dt);
+  for (int r = 2; r <= o.rsplit; ++r) {
+    TimeLevel_update(o.tl);
+    prim_step(o, dt);
+  }
+  int n0_qdp, np1_qdp;
+  TimeLevel_Qdp(o.tl, o.qsplit, n0_qdp, np1_qdp);
+  int bad = vertical_remap(o, dt_remap, o.tl.np1, np1_qdp);
+  // Q = Qdp/dp_np1 :807-822
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < o.nelem; ++e)
+    for (int k = 0; k < o.nlev; ++k) {
+      double dp_np1[16];
+      for (int n = 0; n < 16; ++n)
+        dp_np1[n] = (o.hyai[k + 1] - o.hyai[k]) * o.ps0 + (o.hybi[k + 1] - o.hybi[k]) * o.psv(e, o.tl.np1)[n];
+      for (int q = 0; q < o.qsize; ++q)
+        for (int n = 0; n < 16; ++n)
+          o.Q[(((size_t)e * o.qsize + q) * o.nlev + k) * 16 + n] = o.qdp(e, np1_qdp, q, k)[n] / dp_np1[n];
+    }
+  TimeLevel_update(o.tl);
+  return bad;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C API for the tests (ctypes)
+// ---------------------------------------------------------------------------
+extern "C" {
+
+void orc_divergence_sphere(const double* v, const double* dvv, const double* metdet, const double* rmetdet, const double* dinv,
+                           double* div) {
+  ElemGeo e{metdet, rmetdet, nullptr, nullptr, dinv};
+  divergence_sphere(v, dvv, e, div);
+}
+void orc_gradient_sphere(const double* s, const double* dvv, const double* dinv, double* ds) { gradient_sphere(s, dvv, dinv, ds); }
+void orc_divergence_sphere_wk(const double* v, const double* dvv, const double* spheremp, const double* dinv, double* div) {
+  ElemGeo e{nullptr, nullptr, spheremp, nullptr, dinv};
+  divergence_sphere_wk(v, dvv, e, div);
+}
+void orc_laplace_sphere_wk(const double* s, const double* dvv, const double* spheremp, const double* dinv, double* lap) {
+  ElemGeo e{nullptr, nullptr, spheremp, nullptr, dinv};
+  laplace_sphere_wk(s, dvv, e, lap);
+}
+void orc_limiter_optim_iter_full(double* ptens, const double* sphweights, double* minp, double* maxp, const double* dpmass) {
+  limiter_optim_iter_full(ptens, sphweights, minp, maxp, dpmass);
+}
+void orc_remap_q_ppm(double* Qdp, int nx, int nlev, int qsize, const double* dp1, const double* dp2) {
+  remap_Q_ppm(Qdp, nx, nlev, qsize, dp1, dp2);
+}
+void orc_dcmip_point(int test, double time, double lon, double lat, double z, double* out11) {
+  Pt pt;
+  double p = 0, zz = z;
+  if (test == 11) test1_advection_deformation(time, lon, lat, p, zz, 1, pt);
+  else test1_advection_hadley(time, lon, lat, p, zz, 1, pt);
+  out11[0] = pt.u; out11[1] = pt.v; out11[2] = pt.w; out11[3] = pt.T; out11[4] = pt.phis; out11[5] = pt.ps; out11[6] = pt.rho;
+  out11[7] = pt.q[0]; out11[8] = pt.q[1]; out11[9] = pt.q[2]; out11[10] = pt.q[3];
+  out11[11] = p;
+}
+
+void* orc_create(int nelem, int qsize, int nlev, const double* dvv, const double* spheremp, const double* rspheremp,
+                 const double* metdet, const double* rmetdet, const double* dinv, const double* lat, const double* lon,
+                 const int* putmap, const int* getmap, const int* reverse, int nbuf, const double* hyai, const double* hybi,
+                 const double* hyam, const double* hybm, double nu_q, int rsplit) {
+  Oracle* o = new Oracle;
+  o->nelem = nelem; o->qsize = qsize; o->nlev = nlev; o->nlevp = nlev + 1;
+  o->nu_q = nu_q; o->rsplit = rsplit;
+  size_t n16 = (size_t)nelem * 16;
+  o->dvv.assign(dvv, dvv + 16);
+  o->spheremp.assign(spheremp, spheremp + n16);
+  o->rspheremp.assign(rspheremp, rspheremp + n16);
+  o->metdet.assign(metdet, metdet + n16);
+  o->rmetdet.assign(rmetdet, rmetdet + n16);
+  o->dinv.assign(dinv, dinv + n16 * 4);
+  o->lat.assign(lat, lat + n16);
+  o->lon.assign(lon, lon + n16);
+  o->putmap.assign(putmap, putmap + (size_t)nelem * 8);
+  o->getmap.assign(getmap, getmap + (size_t)nelem * 8);
+  o->reverse.assign(reverse, reverse + (size_t)nelem * 8);
+  o->nbuf = nbuf;
+  o->hyai.assign(hyai, hyai + nlev + 1);
+  o->hybi.assign(hybi, hybi + nlev + 1);
+  o->hyam.assign(hyam, hyam + nlev);
+  o->hybm.assign(hybm, hybm + nlev);
+  o->etam.resize(nlev); o->etai.resize(nlev + 1);
+  for (int k = 0; k < nlev; ++k) o->etam[k] = hyam[k] + hybm[k];         // hybvcoord_mod.F90:170
+  for (int k = 0; k <= nlev; ++k) o->etai[k] = hyai[k] + hybi[k];       // :171
+  o->v.assign(n16 * 3 * nlev * 2, 0.0);
+  o->dp3d.assign(n16 * 3 * nlev, 0.0);
+  o->ps_v.assign(n16 * 3, 0.0);
+  o->Q.assign(n16 * qsize * nlev, 0.0);
+  o->Qdp.assign(n16 * 2 * qsize * nlev, 0.0);
+  o->vn0.assign(n16 * nlev * 2, 0.0);
+  o->dp.assign(n16 * nlev, 0.0);
+  o->divdp.assign(n16 * nlev, 0.0);
+  o->divdp_proj.assign(n16 * nlev, 0.0);
+  o->omega_p.assign(n16 * nlev, 0.0);
+  o->phi.assign(n16 * nlev, 0.0);
+  o->eta_dot_dpdn.assign(n16 * (nlev + 1), 0.0);
+  o->qmin.assign((size_t)nelem * qsize * nlev, 0.0);
+  o->qmax.assign((size_t)nelem * qsize * nlev, 0.0);
+  return o;
+}
+void orc_destroy(void* h) { delete (Oracle*)h; }
+
+// raw pointer to a named field (numpy views it); *count = number of doubles
+double* orc_field(void* h, const char* name, long long* count) {
+  Oracle* o = (Oracle*)h;
+  std::string s(name);
+  std::vector<double>* f = nullptr;
+  if (s == "v") f = &o->v;
+  else if (s == "dp3d") f = &o->dp3d;
+  else if (s == "ps_v") f = &o->ps_v;
+  else if (s == "Q") f = &o->Q;
+  else if (s == "Qdp") f = &o->Qdp;
+  else if (s == "vn0") f = &o->vn0;
+  else if (s == "dp") f = &o->dp;
+  else if (s == "divdp") f = &o->divdp;
+  else if (s == "divdp_proj") f = &o->divdp_proj;
+  else if (s == "omega_p") f = &o->omega_p;
+  else if (s == "phi") f = &o->phi;
+  else if (s == "eta_dot_dpdn") f = &o->eta_dot_dpdn;
+  else if (s == "qmin") f = &o->qmin;
+  else if (s == "qmax") f = &o->qmax;
+  if (!f) { *count = 0; return nullptr; }
+  *count = (long long)f->size();
+  return f->data();
+}
+void orc_get_tl(void* h, int* out4) {
+  Oracle* o = (Oracle*)h;
+  out4[0] = o->tl.nm1; out4[1] = o->tl.n0; out4[2] = o->tl.np1; out4[3] = o->tl.nstep;
+}
+void orc_set_tl(void* h, const int* in4) {
+  Oracle* o = (Oracle*)h;
+  o->tl.nm1 = in4[0]; o->tl.n0 = in4[1]; o->tl.np1 = in4[2]; o->tl.nstep = in4[3];
+}
+void orc_set_params(void* h, double nu_q, int rsplit, int limiter_option, int test_case) {
+  Oracle* o = (Oracle*)h;
+  o->nu_q = nu_q; o->rsplit = rsplit; o->limiter_option = limiter_option; o->test_case = test_case;
+}
+void orc_prim_init2(void* h, int test) { prim_init2(*(Oracle*)h, test); }
+void orc_set_dcmip_fields(void* h, int test, int tlv, double time) { set_dcmip_fields(*(Oracle*)h, test, tlv, time); }
+void orc_prim_step(void* h, double dt) { prim_step(*(Oracle*)h, dt); }
+int orc_prim_run_subcycle(void* h, double dt) { return prim_run_subcycle(*(Oracle*)h, dt); }
+void orc_precompute_divdp(void* h) { precompute_divdp(*(Oracle*)h); }
+void orc_euler_step(void* h, int np1_qdp, int n0_qdp, double dt, int DSSopt, int rhs_multiplier) {
+  euler_step(*(Oracle*)h, np1_qdp, n0_qdp, dt, DSSopt, rhs_multiplier);
+}
+void orc_qdp_time_avg(void* h, int rkstage, int n0_qdp, int np1_qdp) { qdp_time_avg(*(Oracle*)h, rkstage, n0_qdp, np1_qdp); }
+void orc_advec_tracers_remap_rk2(void* h, double dt) { advec_tracers_remap_rk2(*(Oracle*)h, dt); }
+int orc_vertical_remap(void* h, double dt, int np1, int np1_qdp) { return vertical_remap(*(Oracle*)h, dt, np1, np1_qdp); }
+void orc_neighbor_minmax(void* h) { neighbor_minmax(*(Oracle*)h); }
+// DSS of nlyr planes per element held in `field` ([e][nlyr][16]); used by tests
+void orc_dss(void* h, double* field, int nlyr) {
+  Oracle& o = *(Oracle*)h;
+  ensure_buf(o, nlyr);
+  for (int e = 0; e < o.nelem; ++e) edgeVpack(o, field + (size_t)e * nlyr * 16, nlyr, 0, e);
+  for (int e = 0; e < o.nelem; ++e) edgeVunpack(o, field + (size_t)e * nlyr * 16, nlyr, 0, e);
+}
+// global_integral (global_norms_mod.F90:39-86) of h[e][16]; the cross-element
+// sum is repro_sum's order-free fixed-point sum -> long double accumulation here.
+double orc_global_integral(void* hh, const double* h, const double* mp16) {
+  Oracle& o = *(Oracle*)hh;
+  long double tot = 0;
+  for (int e = 0; e < o.nelem; ++e) {
+    double J = 0;
+    for (int j = 0; j < NP; ++j)
+      for (int i = 0; i < NP; ++i) {
+        double da = mp16[IX(i, j)] * o.metdet[(size_t)e * 16 + IX(i, j)];
+        J = J + da * h[(size_t)e * 16 + IX(i, j)];
+      }
+    tot += J;
+  }
+  return (double)tot / (4.0 * DD_PI);
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+"""In-tree builds: host mesh library (g++) and the CUDA C-ABI library (nvcc, sm_100a)."""
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+ROOT = os.path.dirname(_HERE)
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return r.stdout
+
+
+def build_host(force=False):
+    out = os.path.join(_HERE, "libtse_host.so")
+    srcs = [os.path.join(CSRC, "tse_mesh.cpp"), os.path.join(CSRC, "tse_mesh.hpp")]
+    if force or _newer(out, srcs):
+        _run(["g++", "-O2", "-std=gnu++17", "-fopenmp", "-fPIC", "-shared", "-o", out, srcs[0], "-lquadmath"])
+    return out
+
+
+def cuda_sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def build_cuda(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -> libtse_cuda.so (cross-compiles without a GPU)."""
+    out = os.path.join(_HERE, "libtse_cuda.so")
+    srcs = cuda_sources()
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp", ".h"))]
+    deps.append(os.path.join(ROOT, "include", "tse.h"))
+    if force or _newer(out, deps):
+        cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+               "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        cmd += ["-o", out] + srcs + ["-lnccl"]
+        log = _run(cmd)
+        if verbose:
+            print(log)
+    return out
+
+
+def build_oracle(force=False):
+    """Test infrastructure only (see oracle/oracle.cpp header)."""
+    odir = os.path.join(ROOT, "oracle")
+    out = os.path.join(odir, "_build", "liboracle.so")
+    src = os.path.join(odir, "oracle.cpp")
+    if force or _newer(out, [src]):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        _run(["g++", "-O3", "-march=x86-64-v3", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-o", out, src])
+    return out

@@ -1,0 +1,549 @@
+// C ABI of the B200 tracer-advection path (see include/tse.h for the reference hooks each entry replaces).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "tse.h"
+#include "tse_kernels.cuh"
+#include "tse_remap.cuh"
+
+using namespace tse;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define CU(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t _e = (call);                                                                           \
+    if (_e != cudaSuccess) return fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+const double kRearth = 6.376e6;  // physical_constants.F90:16-34
+const double kRrearth = 1.0 / kRearth;
+
+}  // namespace
+
+struct tse_state {
+  tse_config cfg{};
+  int nelem = 0, ngroups = 0, npad = 0, Q = 0;
+  cudaStream_t stream = nullptr;
+  Geo geo{};
+  Dvv dvv{};
+  std::vector<int> h2i;  // host element -> internal element
+  int* d_h2i = nullptr;
+  // tracer buffers: 2 time levels + stage ping-pong + biharmonic temporary
+  double* qbuf[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t qdoubles = 0;
+  int slot_buf[3] = {-1, 0, 1};      // [tl] (1-based) -> buffer
+  int slot_pending[3] = {0, 0, 0};   // [tl] buffer holds pre-DSS values
+  // level fields
+  size_t ldoubles = 0;
+  double *vn0 = nullptr, *dp = nullptr, *divdp = nullptr, *divdp_proj = nullptr, *eta_dot = nullptr, *omega_p = nullptr,
+         *lev_tmp = nullptr, *dp3d = nullptr, *ps_v = nullptr, *pkg = nullptr;
+  double *qmin = nullptr, *qmax = nullptr, *qmin_loc = nullptr, *qmax_loc = nullptr;
+  double *d_dp0 = nullptr, *d_dA = nullptr, *d_dB = nullptr;
+  double hyai0_ps0 = 0;
+  double* stage = nullptr;
+  size_t stage_doubles = 0;
+  int* d_err = nullptr;
+  long long launches = 0;
+  long long dev_bytes = 0;
+  std::vector<void*> allocs;
+  std::map<std::string, double> timers;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+template <class T>
+int dalloc(tse_state* s, T** p, size_t count) {
+  void* v = nullptr;
+  CU(cudaMalloc(&v, count * sizeof(T)));
+  CU(cudaMemsetAsync(v, 0, count * sizeof(T), s->stream));
+  s->allocs.push_back(v);
+  s->dev_bytes += (long long)(count * sizeof(T));
+  *p = (T*)v;
+  return 0;
+}
+template <class T>
+int upload(tse_state* s, T** p, const std::vector<T>& h) {
+  if (dalloc(s, p, h.size())) return 1;
+  CU(cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+inline int edge_node(int d, int t) {
+  switch (d) {
+    case SOUTH: return t;
+    case EAST: return 3 + 4 * t;
+    case NORTH: return 12 + t;
+    default: return 4 * t;
+  }
+}
+inline int corner_node(int d) { return d == SWEST ? 0 : d == SEAST ? 3 : d == NWEST ? 12 : 15; }
+
+dim3 plane_grid(const tse_state* s) { return dim3((unsigned)(s->ngroups * NKC), (unsigned)((s->Q + QPB - 1) / QPB)); }
+unsigned level_blocks(const tse_state* s) { return (unsigned)(((size_t)s->ngroups * NKC * GPL + 127) / 128); }
+
+DssView view(const tse_state* s, int buf, int pending) {
+  DssView v;
+  v.q = s->qbuf[buf];
+  v.ghost = nullptr;
+  v.pending = pending;
+  v.Q = s->Q;
+  return v;
+}
+MinMaxIO mmio(const tse_state* s) {
+  MinMaxIO m;
+  m.qmin = s->qmin; m.qmax = s->qmax; m.qmin_loc = s->qmin_loc; m.qmax_loc = s->qmax_loc; m.ghost_mm = nullptr;
+  return m;
+}
+
+int pick_buffer(const tse_state* s, std::initializer_list<int> protect) {
+  for (int b = 0; b < 4; ++b) {
+    bool ok = true;
+    for (int p : protect)
+      if (p == b) ok = false;
+    if (ok) return b;
+  }
+  return -1;
+}
+
+int check_tl(int tl) { return (tl == 1 || tl == 2) ? 0 : fail("time level %d out of range (1|2)", tl); }
+
+int resolve_slot(tse_state* s, int tl) {
+  if (!s->slot_pending[tl]) return 0;
+  const int other = s->slot_buf[3 - tl];
+  const int in = s->slot_buf[tl];
+  const int out = pick_buffer(s, {in, other});
+  k_resolve<<<plane_grid(s), GPL * QPB, 0, s->stream>>>(s->geo, view(s, in, 1), s->qbuf[out]);
+  ++s->launches;
+  CU(cudaGetLastError());
+  s->slot_buf[tl] = out;
+  s->slot_pending[tl] = 0;
+  return 0;
+}
+
+int check_device_error(tse_state* s) {
+  int flag = 0;
+  CU(cudaMemcpyAsync(&flag, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (flag) return fail("vertical_remap: negative layer thickness.  timestep or remap time too large");  // prim_advection_mod.F90:1323
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tse_last_error(void) { return g_err.c_str(); }
+
+int tse_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connectivity* conn, const tse_hvcoord* hv, const double* dvv,
+             tse_handle* out) {
+  if (!cfg || !geom || !conn || !hv || !dvv || !out) return fail("tse_init: null argument");
+  if (cfg->np != NP || cfg->nlev != NLEV) return fail("tse_init: built for np=4, nlev=72 (got np=%d nlev=%d)", cfg->np, cfg->nlev);
+  if (cfg->limiter_option != 8) return fail("tse_init: only limiter_option=8 is implemented (got %d)", cfg->limiter_option);
+  if (cfg->hypervis_subcycle_q != 1) return fail("tse_init: limiter 8 requires hypervis_subcycle_q=1 (namelist_mod.F90:688-692)");
+  if (cfg->vert_remap_q_alg == 2) return fail("tse_init: vert_remap_q_alg=2 is not implemented");
+  if (cfg->qsize < 1 || cfg->qsize > cfg->qsize_d) return fail("tse_init: qsize=%d qsize_d=%d", cfg->qsize, cfg->qsize_d);
+  if (cfg->nelemd < 1) return fail("tse_init: nelemd=%d", cfg->nelemd);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("tse_init: no CUDA device (this library has no CPU path)");
+  if (cfg->device >= 0) CU(cudaSetDevice(cfg->device));
+
+  tse_state* s = new tse_state;
+  s->cfg = *cfg;
+  s->nelem = cfg->nelemd;
+  s->ngroups = (s->nelem + GE - 1) / GE;
+  s->npad = s->ngroups * GE;
+  s->Q = cfg->qsize;
+  CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&s->ev0));
+  CU(cudaEventCreate(&s->ev1));
+  std::memcpy(s->dvv.d, dvv, sizeof s->dvv.d);
+  const int ne = s->nelem;
+
+  // internal element order: along the space-filling curve when the host provides it
+  std::vector<int> order(ne);
+  std::iota(order.begin(), order.end(), 0);
+  if (conn->sfc_index) std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return conn->sfc_index[a] < conn->sfc_index[b]; });
+  s->h2i.assign(ne, 0);
+  for (int i = 0; i < ne; ++i) s->h2i[order[i]] = i;
+  if (upload(s, &s->d_h2i, s->h2i)) return 1;
+
+  // geometry
+  const size_t n16 = (size_t)s->npad * 16;
+  std::vector<double> sp(n16, 1.0), rsp(n16, 1.0), rmp(n16, 1.0), rmr(n16, 0.0), mD((size_t)s->npad * 64, 0.0), T((size_t)s->npad * 48, 0.0);
+  for (int eh = 0; eh < ne; ++eh) {
+    const int e = s->h2i[eh];
+    for (int n = 0; n < 16; ++n) {
+      const size_t hi = (size_t)eh * 16 + n, di = (size_t)e * 16 + n;
+      sp[di] = geom->spheremp[hi];
+      rsp[di] = geom->rspheremp[hi];
+      rmp[di] = 1.0 / geom->spheremp[hi];
+      rmr[di] = geom->rmetdet[hi] * kRrearth;
+      const double* Di = geom->Dinv + hi * 4;  // Dinv(a,b) at [a + 2b]
+      const double d11 = Di[0], d21 = Di[1], d12 = Di[2], d22 = Di[3];
+      const double md = geom->metdet[hi];
+      mD[(size_t)e * 64 + n] = md * d11;
+      mD[(size_t)e * 64 + 16 + n] = md * d12;
+      mD[(size_t)e * 64 + 32 + n] = md * d21;
+      mD[(size_t)e * 64 + 48 + n] = md * d22;
+      const double f = geom->spheremp[hi] * kRrearth * kRrearth;
+      T[(size_t)e * 48 + n] = f * (d11 * d11 + d12 * d12);
+      T[(size_t)e * 48 + 16 + n] = f * (d11 * d21 + d12 * d22);
+      T[(size_t)e * 48 + 32 + n] = f * (d21 * d21 + d22 * d22);
+    }
+  }
+  double *d_sp, *d_rsp, *d_rmp, *d_rmr, *d_mD, *d_T;
+  if (upload(s, &d_sp, sp) || upload(s, &d_rsp, rsp) || upload(s, &d_rmp, rmp) || upload(s, &d_rmr, rmr) || upload(s, &d_mD, mD) ||
+      upload(s, &d_T, T))
+    return 1;
+
+  // DSS gather table from the reference's put/get maps (edge_mod.F90:366-511 pack, :648-742 unpack)
+  const int nbuf = conn->nbuf;
+  std::vector<int> slot_src(nbuf, -1);
+  std::vector<char> remote(nbuf, 0);
+  std::vector<int> ghost_base(nbuf, -1);
+  int nghost = 0;
+  for (int c = 0; c < conn->ncycles; ++c)
+    for (int i = 0; i < conn->cyc_len[c]; ++i) {
+      remote[conn->cyc_ptr[c] + i] = 1;
+      ghost_base[conn->cyc_ptr[c] + i] = nghost++;
+    }
+  for (int eh = 0; eh < ne; ++eh)
+    for (int d = 0; d < 8; ++d) {
+      const int pm = conn->putmapP[eh * 8 + d];
+      if (pm < 0) continue;
+      const int len = d < 4 ? NP : 1;
+      if (pm + len > nbuf) return fail("tse_init: putmapP out of range");
+      for (int i = 0; i < len; ++i) {
+        const int t = (d < 4) ? (conn->reverse[eh * 8 + d] ? NP - 1 - i : i) : 0;
+        const int node = d < 4 ? edge_node(d, t) : corner_node(d);
+        if (!remote[pm + i]) slot_src[pm + i] = (s->h2i[eh] << 4) | node;
+      }
+    }
+  std::vector<int> gsrc((size_t)s->npad * NSLOT, -1), nbr8((size_t)s->npad * 8, -1);
+  const int unpack_edges[4] = {SOUTH, EAST, NORTH, WEST};
+  const int unpack_corners[4] = {SWEST, SEAST, NEAST, NWEST};
+  for (int eh = 0; eh < ne; ++eh) {
+    const int e = s->h2i[eh];
+    auto src_of = [&](int b) -> int {
+      if (b < 0 || b >= nbuf) return -1;
+      if (remote[b]) return -(ghost_base[b] + 2);
+      return slot_src[b];
+    };
+    for (int x = 0; x < 4; ++x) {
+      const int gm = conn->getmapP[eh * 8 + unpack_edges[x]];
+      for (int i = 0; i < 4; ++i) gsrc[(size_t)e * NSLOT + 4 * x + i] = gm < 0 ? -1 : src_of(gm + i);
+      const int b = gm < 0 ? -1 : src_of(gm);
+      nbr8[(size_t)e * 8 + x] = b >= 0 ? (b >> 4) : -1;  // ghosts: filled by tse_comm_init
+    }
+    for (int x = 0; x < 4; ++x) {
+      const int gm = conn->getmapP[eh * 8 + unpack_corners[x]];
+      const int b = gm < 0 ? -1 : src_of(gm);
+      gsrc[(size_t)e * NSLOT + 16 + x] = b;
+      nbr8[(size_t)e * 8 + 4 + x] = b >= 0 ? (b >> 4) : -1;
+    }
+  }
+  if (conn->ncycles > 0) return fail("tse_init: multi-rank connectivity needs tse_comm_init (not in this build yet)");
+  int *d_gsrc, *d_nbr8;
+  if (upload(s, &d_gsrc, gsrc) || upload(s, &d_nbr8, nbr8)) return 1;
+  s->geo.spheremp = d_sp; s->geo.rspheremp = d_rsp; s->geo.rmp = d_rmp; s->geo.rmr = d_rmr; s->geo.mD = d_mD; s->geo.T = d_T;
+  s->geo.gsrc = d_gsrc; s->geo.nbr8 = d_nbr8; s->geo.nelem = ne; s->geo.ngroups = s->ngroups;
+
+  // vertical coordinate
+  std::vector<double> dp0(NLEV), dA(NLEV), dB(NLEV);
+  for (int k = 0; k < NLEV; ++k) {
+    dA[k] = (hv->hyai[k + 1] - hv->hyai[k]) * hv->ps0;
+    dB[k] = hv->hybi[k + 1] - hv->hybi[k];
+    dp0[k] = (hv->hyai[k + 1] - hv->hyai[k]) * hv->ps0 + (hv->hybi[k + 1] - hv->hybi[k]) * hv->ps0;  // prim_advection_mod.F90:818-820
+  }
+  s->hyai0_ps0 = hv->hyai[0] * hv->ps0;
+  if (upload(s, &s->d_dp0, dp0) || upload(s, &s->d_dA, dA) || upload(s, &s->d_dB, dB)) return 1;
+
+  // state
+  s->ldoubles = (size_t)s->ngroups * NKC * GPL * 16;
+  s->qdoubles = s->ldoubles * s->Q;
+  for (int b = 0; b < 4; ++b)
+    if (dalloc(s, &s->qbuf[b], s->qdoubles)) return 1;
+  if (dalloc(s, &s->vn0, 2 * s->ldoubles) || dalloc(s, &s->dp, s->ldoubles) || dalloc(s, &s->divdp, s->ldoubles) ||
+      dalloc(s, &s->divdp_proj, s->ldoubles) || dalloc(s, &s->eta_dot, s->ldoubles) || dalloc(s, &s->omega_p, s->ldoubles) ||
+      dalloc(s, &s->lev_tmp, s->ldoubles) || dalloc(s, &s->dp3d, s->ldoubles) || dalloc(s, &s->ps_v, (size_t)s->npad * 16) ||
+      dalloc(s, &s->pkg, NPKG * s->ldoubles))
+    return 1;
+  const size_t nplanes = s->qdoubles / 16;
+  if (dalloc(s, &s->qmin, nplanes) || dalloc(s, &s->qmax, nplanes) || dalloc(s, &s->qmin_loc, nplanes) || dalloc(s, &s->qmax_loc, nplanes))
+    return 1;
+  if (dalloc(s, &s->d_err, 1)) return 1;
+  // staging buffer for host<->device layout conversion: whole elements, at most ~256 MB
+  {
+    const size_t per_elem = (size_t)16 * NLEV * std::max(s->Q, 2) + 16;
+    size_t ne_chunk = std::max<size_t>(1, std::min<size_t>(ne, ((size_t)32 << 20) / per_elem));
+    s->stage_doubles = ne_chunk * per_elem;
+    if (dalloc(s, &s->stage, s->stage_doubles)) return 1;
+  }
+  CU(cudaFuncSetAttribute(k_vertical_remap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RM_SMEM));
+  CU(cudaStreamSynchronize(s->stream));
+  *out = s;
+  return 0;
+}
+
+int tse_finalize(tse_handle s) {
+  if (!s) return 0;
+  cudaStreamSynchronize(s->stream);
+  for (void* p : s->allocs) cudaFree(p);
+  cudaEventDestroy(s->ev0);
+  cudaEventDestroy(s->ev1);
+  cudaStreamDestroy(s->stream);
+  delete s;
+  return 0;
+}
+
+int tse_synchronize(tse_handle s) {
+  CU(cudaStreamSynchronize(s->stream));
+  return check_device_error(s);
+}
+
+int tse_comm_unique_id(void*) { return fail("tse_comm_unique_id: multi-GPU exchange not in this build yet"); }
+int tse_comm_init(tse_handle, int, int, const void*) { return fail("tse_comm_init: multi-GPU exchange not in this build yet"); }
+
+// ---- host <-> device copies -------------------------------------------------------------------
+static int qdp_copy(tse_state* s, double* host, long long elem_stride, int tl, int to_device) {
+  if (check_tl(tl)) return 1;
+  if (!to_device && resolve_slot(s, tl)) return 1;
+  const size_t per_elem = (size_t)16 * NLEV * s->Q;
+  const size_t ne_chunk = s->stage_doubles / per_elem;
+  const size_t tl_off = (size_t)(tl - 1) * 16 * NLEV * s->cfg.qsize_d;
+  double* dev = s->qbuf[s->slot_buf[tl]];
+  for (size_t e0 = 0; e0 < (size_t)s->nelem; e0 += ne_chunk) {
+    const size_t n = std::min(ne_chunk, (size_t)s->nelem - e0);
+    double* h = host + e0 * (size_t)elem_stride + tl_off;
+    const unsigned blocks = (unsigned)((n * per_elem / 2 + 255) / 256);
+    if (to_device) {
+      CU(cudaMemcpy2DAsync(s->stage, per_elem * 8, h, (size_t)elem_stride * 8, per_elem * 8, n, cudaMemcpyHostToDevice, s->stream));
+      k_qdp_relayout<<<blocks, 256, 0, s->stream>>>(dev, s->stage, s->d_h2i, (int)e0, (int)n, s->Q, 1);
+      ++s->launches;
+    } else {
+      k_qdp_relayout<<<blocks, 256, 0, s->stream>>>(dev, s->stage, s->d_h2i, (int)e0, (int)n, s->Q, 0);
+      ++s->launches;
+      CU(cudaMemcpy2DAsync(h, (size_t)elem_stride * 8, s->stage, per_elem * 8, per_elem * 8, n, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->stream));
+  }
+  if (to_device) s->slot_pending[tl] = 0;
+  return 0;
+}
+
+int tse_copy_qdp_h2d(tse_handle s, const double* qdp, long long elem_stride, int tl) {
+  return qdp_copy(s, const_cast<double*>(qdp), elem_stride, tl, 1);
+}
+int tse_copy_qdp_d2h(tse_handle s, double* qdp, long long elem_stride, int tl) { return qdp_copy(s, qdp, elem_stride, tl, 0); }
+
+static int level_copy(tse_state* s, double* dev, double* host, long long stride, int ncomp, int host_nlev, int to_device) {
+  if (!host) return 0;
+  const size_t per_elem = (size_t)16 * ncomp * host_nlev;
+  const size_t ne_chunk = s->stage_doubles / per_elem;
+  for (size_t e0 = 0; e0 < (size_t)s->nelem; e0 += ne_chunk) {
+    const size_t n = std::min(ne_chunk, (size_t)s->nelem - e0);
+    double* h = host + e0 * (size_t)stride;
+    const unsigned blocks = (unsigned)((n * 16 * ncomp * NLEV / 2 + 255) / 256);
+    if (to_device) {
+      CU(cudaMemcpy2DAsync(s->stage, per_elem * 8, h, (size_t)stride * 8, per_elem * 8, n, cudaMemcpyHostToDevice, s->stream));
+      k_level_relayout<<<blocks, 256, 0, s->stream>>>(dev, s->stage, s->d_h2i + e0, (int)n, ncomp, host_nlev, 1);
+      ++s->launches;
+    } else {
+      // keep host levels beyond NLEV (eta_dot_dpdn(nlev+1)) untouched: copy only the first NLEV*ncomp planes
+      k_level_relayout<<<blocks, 256, 0, s->stream>>>(dev, s->stage, s->d_h2i + e0, (int)n, ncomp, host_nlev, 0);
+      ++s->launches;
+      CU(cudaMemcpy2DAsync(h, (size_t)stride * 8, s->stage, per_elem * 8, (size_t)16 * ncomp * NLEV * 8, n, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->stream));
+  }
+  return 0;
+}
+
+int tse_set_derived(tse_handle s, const double* vn0, long long s_vn0, const double* dp, long long s_dp, const double* eta, long long s_eta,
+                    const double* omega, long long s_omega) {
+  if (level_copy(s, s->vn0, const_cast<double*>(vn0), s_vn0, 2, NLEV, 1)) return 1;
+  if (level_copy(s, s->dp, const_cast<double*>(dp), s_dp, 1, NLEV, 1)) return 1;
+  if (level_copy(s, s->eta_dot, const_cast<double*>(eta), s_eta, 1, NLEV + 1, 1)) return 1;
+  if (level_copy(s, s->omega_p, const_cast<double*>(omega), s_omega, 1, NLEV, 1)) return 1;
+  return 0;
+}
+
+int tse_get_derived(tse_handle s, double* divdp, long long s_divdp, double* proj, long long s_proj, double* eta, long long s_eta,
+                    double* omega, long long s_omega) {
+  if (level_copy(s, s->divdp, divdp, s_divdp, 1, NLEV, 0)) return 1;
+  if (level_copy(s, s->divdp_proj, proj, s_proj, 1, NLEV, 0)) return 1;
+  if (level_copy(s, s->eta_dot, eta, s_eta, 1, NLEV + 1, 0)) return 1;
+  if (level_copy(s, s->omega_p, omega, s_omega, 1, NLEV, 0)) return 1;
+  return 0;
+}
+
+int tse_get_dp3d_ps(tse_handle s, double* dp3d, long long s_dp3d, double* ps_v, long long s_ps) {
+  if (level_copy(s, s->dp3d, dp3d, s_dp3d, 1, NLEV, 0)) return 1;
+  if (ps_v) {
+    std::vector<double> tmp((size_t)s->npad * 16);
+    CU(cudaMemcpyAsync(tmp.data(), s->ps_v, tmp.size() * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    for (int eh = 0; eh < s->nelem; ++eh) std::memcpy(ps_v + (size_t)eh * s_ps, &tmp[(size_t)s->h2i[eh] * 16], 16 * 8);
+  }
+  return 0;
+}
+
+int tse_get_qminmax(tse_handle s, double* qmin, double* qmax) {
+  const size_t cnt = (size_t)s->nelem * s->Q * NLEV;
+  if (cnt > s->stage_doubles) return fail("tse_get_qminmax: staging buffer too small");
+  for (int w = 0; w < 2; ++w) {
+    double* h = w ? qmax : qmin;
+    if (!h) continue;
+    k_scalar_to_host<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(w ? s->qmax : s->qmin, s->stage, s->d_h2i, s->nelem, s->Q);
+    ++s->launches;
+    CU(cudaMemcpyAsync(h, s->stage, cnt * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+  }
+  return 0;
+}
+
+// ---- the path ---------------------------------------------------------------------------------
+int tse_precompute_divdp(tse_handle s) {
+  k_divdp<<<level_blocks(s), 128, 0, s->stream>>>(s->geo, s->dvv, s->vn0, s->divdp, s->divdp_proj);
+  ++s->launches;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int tse_euler_step(tse_handle s, int np1_qdp, int n0_qdp, double dt, int DSSopt, int rhs_multiplier) {
+  if (check_tl(np1_qdp) || check_tl(n0_qdp)) return 1;
+  if (rhs_multiplier < 0 || rhs_multiplier > 2) return fail("tse_euler_step: rhs_multiplier=%d", rhs_multiplier);
+  const int in = s->slot_buf[n0_qdp], in_pending = s->slot_pending[n0_qdp];
+  const dim3 grid = plane_grid(s);
+  const int threads = GPL * QPB;
+  k_stage_prep<<<level_blocks(s), 128, 0, s->stream>>>(s->geo, s->vn0, s->dp, s->divdp, s->divdp_proj, rhs_multiplier * dt, dt, s->pkg,
+                                                       s->ldoubles);
+  ++s->launches;
+  StageArgs a;
+  a.in = view(s, in, in_pending);
+  a.qtens = view(s, in, 0);
+  a.pkg = s->pkg;
+  a.pkg_stride = s->ldoubles;
+  a.mm = mmio(s);
+  a.dt = dt;
+  a.visc_coef = -3.0 * dt * s->cfg.nu_q;  // rhs_viss = 3 (prim_advection_mod.F90:797,823)
+  a.dp0 = s->d_dp0;
+  const int other = (np1_qdp == n0_qdp) ? s->slot_buf[3 - np1_qdp] : -1;  // the untouched time level
+  int tmp = -1;
+  if (rhs_multiplier == 0) {
+    k_minmax_local<<<grid, threads, 0, s->stream>>>(s->geo, a.in, s->pkg, s->ldoubles, a.mm);
+    ++s->launches;
+  } else if (rhs_multiplier == 2) {
+    tmp = pick_buffer(s, {in, other, np1_qdp == n0_qdp ? -1 : s->slot_buf[n0_qdp]});
+    if (tmp < 0) return fail("tse_euler_step: no free tracer buffer");
+    k_biharm_pre<<<grid, threads, 0, s->stream>>>(s->geo, s->dvv, a.in, s->pkg, s->ldoubles, a.mm, s->qbuf[tmp]);
+    ++s->launches;
+    a.qtens = view(s, tmp, 1);
+  }
+  const int outb = pick_buffer(s, {in, other, tmp});
+  if (outb < 0) return fail("tse_euler_step: no free tracer buffer");
+  a.out = s->qbuf[outb];
+  if (rhs_multiplier == 0) k_euler_stage<1><<<grid, threads, 0, s->stream>>>(s->geo, s->dvv, a);
+  else if (rhs_multiplier == 1) k_euler_stage<2><<<grid, threads, 0, s->stream>>>(s->geo, s->dvv, a);
+  else k_euler_stage<3><<<grid, threads, 0, s->stream>>>(s->geo, s->dvv, a);
+  ++s->launches;
+  CU(cudaGetLastError());
+  s->slot_buf[np1_qdp] = outb;
+  s->slot_pending[np1_qdp] = 1;
+
+  // DSS of the extra level field (prim_advection_mod.F90:913-919, 943-958)
+  double** f = DSSopt == TSE_DSS_ETA ? &s->eta_dot : DSSopt == TSE_DSS_OMEGA ? &s->omega_p : DSSopt == TSE_DSS_DIV_VDP_AVE ? &s->divdp_proj : nullptr;
+  if (DSSopt != TSE_DSS_NO_VAR && !f) return fail("tse_euler_step: DSSopt=%d", DSSopt);
+  if (f) {
+    k_dss_level<<<level_blocks(s), 128, 0, s->stream>>>(s->geo, *f, nullptr, s->lev_tmp);
+    ++s->launches;
+    CU(cudaGetLastError());
+    std::swap(*f, s->lev_tmp);
+  }
+  return 0;
+}
+
+int tse_qdp_time_avg(tse_handle s, int rkstage, int n0_qdp, int np1_qdp) {
+  if (check_tl(np1_qdp) || check_tl(n0_qdp) || n0_qdp == np1_qdp) return fail("tse_qdp_time_avg: bad time levels %d %d", n0_qdp, np1_qdp);
+  if (resolve_slot(s, n0_qdp)) return 1;
+  const int in = s->slot_buf[np1_qdp], q0 = s->slot_buf[n0_qdp];
+  const int outb = pick_buffer(s, {in, q0});
+  k_time_avg<<<plane_grid(s), GPL * QPB, 0, s->stream>>>(s->geo, view(s, in, s->slot_pending[np1_qdp]), s->qbuf[q0], (double)rkstage,
+                                                         s->qbuf[outb]);
+  ++s->launches;
+  CU(cudaGetLastError());
+  s->slot_buf[np1_qdp] = outb;
+  s->slot_pending[np1_qdp] = 0;
+  return 0;
+}
+
+int tse_vertical_remap(tse_handle s, double dt, int np1, int np1_qdp) {
+  (void)np1;  // the device keeps a single copy of dp3d/ps_v: the one of time level np1
+  if (check_tl(np1_qdp)) return 1;
+  if (resolve_slot(s, np1_qdp)) return 1;
+  RemapArgs a;
+  a.q = s->qbuf[s->slot_buf[np1_qdp]];
+  a.dp = s->dp; a.divdp_proj = s->divdp_proj; a.dp3d = s->dp3d; a.ps_v = s->ps_v;
+  a.dA = s->d_dA; a.dB = s->d_dB; a.hyai0_ps0 = s->hyai0_ps0; a.dt = dt; a.Q = s->Q; a.nelem = s->nelem; a.error_flag = s->d_err;
+  k_vertical_remap<<<s->nelem, RM_THREADS, RM_SMEM, s->stream>>>(a);
+  ++s->launches;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int tse_advec_tracers_remap_rk2(tse_handle s, double dt, int nstep) {
+  // TimeLevel_Qdp (time_mod.F90:85-109)
+  const int qsplit = s->cfg.qsplit > 0 ? s->cfg.qsplit : 1;
+  const int n0 = ((nstep / qsplit) % 2 == 0) ? 1 : 2, np1 = 3 - n0;
+  if (tse_precompute_divdp(s)) return 1;
+  if (tse_euler_step(s, np1, n0, dt / 2, TSE_DSS_DIV_VDP_AVE, 0)) return 1;
+  if (tse_euler_step(s, np1, np1, dt / 2, TSE_DSS_ETA, 1)) return 1;
+  if (tse_euler_step(s, np1, np1, dt / 2, TSE_DSS_OMEGA, 2)) return 1;
+  return tse_qdp_time_avg(s, 3, n0, np1);
+}
+
+int tse_dcmip_init(tse_handle, int) { return fail("tse_dcmip_init: not in this build yet"); }
+int tse_prim_run_subcycle(tse_handle, double, int*) { return fail("tse_prim_run_subcycle: not in this build yet"); }
+int tse_diag_mass(tse_handle, int, double*) { return fail("tse_diag_mass: not in this build yet"); }
+int tse_diag_qminmax(tse_handle, int, double*, double*) { return fail("tse_diag_qminmax: not in this build yet"); }
+
+double tse_timer_ms(tse_handle s, const char* name) {
+  auto it = s->timers.find(name);
+  return it == s->timers.end() ? -1.0 : it->second;
+}
+long long tse_launch_count(tse_handle s) { return s->launches; }
+long long tse_device_bytes(tse_handle s) { return s->dev_bytes; }
+
+}  // extern "C"
