@@ -142,6 +142,13 @@ int tse_diag_qminmax(tse_handle h, int tl, double* qmin /* [qsize] */, double* q
 /* timers: CUDA-event time (ms) accumulated under the reference's GPTL timer names
  * ("prim_advec_tracers_remap_rk2", "euler_step", "vertical_remap", "prim_advance_exp"); returns <0 if unknown */
 double tse_timer_ms(tse_handle h, const char* name);
+int tse_timer_reset(tse_handle h);
+/* CUDA events on the handle's own stream (torch.cuda.Event only sees torch's stream): record slot 0..15, elapsed ms a->b */
+int tse_mark(tse_handle h, int slot);
+double tse_mark_elapsed_ms(tse_handle h, int a, int b);
+/* derived%vn0 / derived%dp as currently held on the device (e.g. after the device-side prim_advance_exp) */
+int tse_get_wind(tse_handle h, double* vn0, long long s_vn0, double* dp, long long s_dp);
+long long tse_stage_launch_count(tse_handle h);
 /* number of kernel launches issued by this handle so far */
 long long tse_launch_count(tse_handle h);
 /* device bytes allocated by this handle */

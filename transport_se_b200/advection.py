@@ -47,7 +47,7 @@ EXPORTS = ["tse_last_error", "tse_device_count", "tse_init", "tse_finalize", "ts
            "tse_copy_qdp_h2d", "tse_copy_qdp_d2h", "tse_set_derived", "tse_get_derived", "tse_get_dp3d_ps", "tse_get_qminmax",
            "tse_precompute_divdp", "tse_euler_step", "tse_qdp_time_avg", "tse_vertical_remap", "tse_advec_tracers_remap_rk2",
            "tse_dcmip_init", "tse_prim_run_subcycle", "tse_diag_mass", "tse_diag_qminmax", "tse_timer_ms", "tse_launch_count",
-           "tse_device_bytes"]
+           "tse_device_bytes", "tse_timer_reset", "tse_mark", "tse_mark_elapsed_ms", "tse_get_wind", "tse_stage_launch_count"]
 
 
 def cuda_lib():
@@ -87,6 +87,13 @@ def cuda_lib():
         L.tse_launch_count.restype = ll
         L.tse_device_bytes.argtypes = [vp]
         L.tse_device_bytes.restype = ll
+        L.tse_stage_launch_count.argtypes = [vp]
+        L.tse_stage_launch_count.restype = ll
+        L.tse_timer_reset.argtypes = [vp]
+        L.tse_mark.argtypes = [vp, i]
+        L.tse_mark_elapsed_ms.argtypes = [vp, i, i]
+        L.tse_mark_elapsed_ms.restype = d
+        L.tse_get_wind.argtypes = [vp, _dp, ll, _dp, ll]
         _LIB = L
     return _LIB
 
@@ -207,6 +214,22 @@ class TracerAdvection:
 
     def synchronize(self):
         self._ck(self._L.tse_synchronize(self._h))
+
+    def get_wind(self, vn0=None, dp=None):
+        self._ck(self._L.tse_get_wind(self._h, _p(vn0), _stride(vn0), _p(dp), _stride(dp)))
+
+    def mark(self, slot):
+        self._ck(self._L.tse_mark(self._h, slot))
+
+    def mark_elapsed_ms(self, a, b):
+        return self._L.tse_mark_elapsed_ms(self._h, a, b)
+
+    def timer_reset(self):
+        self._ck(self._L.tse_timer_reset(self._h))
+
+    @property
+    def stage_launch_count(self):
+        return self._L.tse_stage_launch_count(self._h)
 
     def timer_ms(self, name):
         return self._L.tse_timer_ms(self._h, name.encode())

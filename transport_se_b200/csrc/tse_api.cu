@@ -14,6 +14,8 @@
 #include "tse.h"
 #include "tse_kernels.cuh"
 #include "tse_remap.cuh"
+#include "tse_dcmip.cuh"
+#include "tse_diag.cuh"
 
 using namespace tse;
 
@@ -65,11 +67,27 @@ struct tse_state {
   double* stage = nullptr;
   size_t stage_doubles = 0;
   int* d_err = nullptr;
-  long long launches = 0;
+  long long launches = 0, stage_launches = 0;
   long long dev_bytes = 0;
+  cudaEvent_t marks[16] = {};
   std::vector<void*> allocs;
   std::map<std::string, double> timers;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // lazily resolved CUDA-event timers under the reference's GPTL names
+  struct TimerRec { const char* name; cudaEvent_t a, b; };
+  std::vector<TimerRec> timer_pending;
+  std::vector<cudaEvent_t> event_pool;
+  // prescribed-wind test case (tse_dcmip_init)
+  int test_case = 0;
+  double *d_lon = nullptr, *d_lat = nullptr;
+  DcmipTables dcmip{};
+  std::vector<double> hv_hyai, hv_hybi, hv_hyam, hv_hybm;
+  double ps0 = 0;
+  bool have_latlon = false;
+  // diagnostics
+  unsigned long long* d_maxbits = nullptr;
+  long long* d_acc = nullptr;
+  int* d_shift = nullptr;
 };
 
 namespace {
@@ -143,6 +161,44 @@ int resolve_slot(tse_state* s, int tl) {
   s->slot_pending[tl] = 0;
   return 0;
 }
+
+cudaEvent_t get_event(tse_state* s) {
+  if (!s->event_pool.empty()) {
+    cudaEvent_t e = s->event_pool.back();
+    s->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void resolve_timers(tse_state* s) {
+  if (s->timer_pending.empty()) return;
+  cudaStreamSynchronize(s->stream);
+  for (auto& r : s->timer_pending) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    s->timers[r.name] += ms;
+    s->event_pool.push_back(r.a);
+    s->event_pool.push_back(r.b);
+  }
+  s->timer_pending.clear();
+}
+struct ScopedTimer {
+  tse_state* s;
+  tse_state::TimerRec r;
+  ScopedTimer(tse_state* s_, const char* name) : s(s_) {
+    if (s->timer_pending.size() > 8192) resolve_timers(s);
+    r.name = name;
+    r.a = get_event(s);
+    r.b = get_event(s);
+    cudaEventRecord(r.a, s->stream);
+  }
+  ~ScopedTimer() {
+    cudaEventRecord(r.b, s->stream);
+    s->timer_pending.push_back(r);
+  }
+};
 
 int check_device_error(tse_state* s) {
   int flag = 0;
@@ -286,6 +342,24 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
     dp0[k] = (hv->hyai[k + 1] - hv->hyai[k]) * hv->ps0 + (hv->hybi[k + 1] - hv->hybi[k]) * hv->ps0;  // prim_advection_mod.F90:818-820
   }
   s->hyai0_ps0 = hv->hyai[0] * hv->ps0;
+  s->ps0 = hv->ps0;
+  s->hv_hyai.assign(hv->hyai, hv->hyai + NLEV + 1);
+  s->hv_hybi.assign(hv->hybi, hv->hybi + NLEV + 1);
+  if (hv->hyam && hv->hybm) {
+    s->hv_hyam.assign(hv->hyam, hv->hyam + NLEV);
+    s->hv_hybm.assign(hv->hybm, hv->hybm + NLEV);
+  }
+  if (geom->lat && geom->lon) {
+    std::vector<double> la(n16, 0.0), lo(n16, 0.0);
+    for (int eh = 0; eh < ne; ++eh)
+      for (int n = 0; n < 16; ++n) {
+        la[(size_t)s->h2i[eh] * 16 + n] = geom->lat[(size_t)eh * 16 + n];
+        lo[(size_t)s->h2i[eh] * 16 + n] = geom->lon[(size_t)eh * 16 + n];
+      }
+    if (upload(s, &s->d_lat, la) || upload(s, &s->d_lon, lo)) return 1;
+    s->have_latlon = true;
+  }
+  if (dalloc(s, &s->d_maxbits, (size_t)s->Q) || dalloc(s, &s->d_acc, (size_t)2 * s->Q) || dalloc(s, &s->d_shift, (size_t)s->Q)) return 1;
   if (upload(s, &s->d_dp0, dp0) || upload(s, &s->d_dA, dA) || upload(s, &s->d_dB, dB)) return 1;
 
   // state
@@ -318,6 +392,8 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
 int tse_finalize(tse_handle s) {
   if (!s) return 0;
   cudaStreamSynchronize(s->stream);
+  resolve_timers(s);
+  for (cudaEvent_t e : s->event_pool) cudaEventDestroy(e);
   for (void* p : s->allocs) cudaFree(p);
   cudaEventDestroy(s->ev0);
   cudaEventDestroy(s->ev1);
@@ -444,6 +520,7 @@ int tse_precompute_divdp(tse_handle s) {
 
 int tse_euler_step(tse_handle s, int np1_qdp, int n0_qdp, double dt, int DSSopt, int rhs_multiplier) {
   if (check_tl(np1_qdp) || check_tl(n0_qdp)) return 1;
+  ScopedTimer tm(s, "euler_step");
   if (rhs_multiplier < 0 || rhs_multiplier > 2) return fail("tse_euler_step: rhs_multiplier=%d", rhs_multiplier);
   const int in = s->slot_buf[n0_qdp], in_pending = s->slot_pending[n0_qdp];
   const dim3 grid = plane_grid(s);
@@ -475,10 +552,14 @@ int tse_euler_step(tse_handle s, int np1_qdp, int n0_qdp, double dt, int DSSopt,
   const int outb = pick_buffer(s, {in, other, tmp});
   if (outb < 0) return fail("tse_euler_step: no free tracer buffer");
   a.out = s->qbuf[outb];
-  if (rhs_multiplier == 0) k_euler_stage<1><<<grid, threads, 0, s->stream>>>(s->geo, s->dvv, a);
-  else if (rhs_multiplier == 1) k_euler_stage<2><<<grid, threads, 0, s->stream>>>(s->geo, s->dvv, a);
-  else k_euler_stage<3><<<grid, threads, 0, s->stream>>>(s->geo, s->dvv, a);
-  ++s->launches;
+  {
+    ScopedTimer tk(s, "k_euler_stage");
+    if (rhs_multiplier == 0) k_euler_stage<1><<<grid, threads, 0, s->stream>>>(s->geo, s->dvv, a);
+    else if (rhs_multiplier == 1) k_euler_stage<2><<<grid, threads, 0, s->stream>>>(s->geo, s->dvv, a);
+    else k_euler_stage<3><<<grid, threads, 0, s->stream>>>(s->geo, s->dvv, a);
+    ++s->launches;
+    ++s->stage_launches;
+  }
   CU(cudaGetLastError());
   s->slot_buf[np1_qdp] = outb;
   s->slot_pending[np1_qdp] = 1;
@@ -513,6 +594,7 @@ int tse_vertical_remap(tse_handle s, double dt, int np1, int np1_qdp) {
   (void)np1;  // the device keeps a single copy of dp3d/ps_v: the one of time level np1
   if (check_tl(np1_qdp)) return 1;
   if (resolve_slot(s, np1_qdp)) return 1;
+  ScopedTimer tm(s, "vertical_remap");
   RemapArgs a;
   a.q = s->qbuf[s->slot_buf[np1_qdp]];
   a.dp = s->dp; a.divdp_proj = s->divdp_proj; a.dp3d = s->dp3d; a.ps_v = s->ps_v;
@@ -527,6 +609,7 @@ int tse_advec_tracers_remap_rk2(tse_handle s, double dt, int nstep) {
   // TimeLevel_Qdp (time_mod.F90:85-109)
   const int qsplit = s->cfg.qsplit > 0 ? s->cfg.qsplit : 1;
   const int n0 = ((nstep / qsplit) % 2 == 0) ? 1 : 2, np1 = 3 - n0;
+  ScopedTimer tm(s, "prim_advec_tracers_remap_rk2");
   if (tse_precompute_divdp(s)) return 1;
   if (tse_euler_step(s, np1, n0, dt / 2, TSE_DSS_DIV_VDP_AVE, 0)) return 1;
   if (tse_euler_step(s, np1, np1, dt / 2, TSE_DSS_ETA, 1)) return 1;
@@ -534,16 +617,120 @@ int tse_advec_tracers_remap_rk2(tse_handle s, double dt, int nstep) {
   return tse_qdp_time_avg(s, 3, n0, np1);
 }
 
-int tse_dcmip_init(tse_handle, int) { return fail("tse_dcmip_init: not in this build yet"); }
-int tse_prim_run_subcycle(tse_handle, double, int*) { return fail("tse_prim_run_subcycle: not in this build yet"); }
-int tse_diag_mass(tse_handle, int, double*) { return fail("tse_diag_mass: not in this build yet"); }
+int tse_dcmip_init(tse_handle s, int test_case) {
+  if (test_case != 11 && test_case != 12) return fail("tse_dcmip_init: test_case must be 11 (DCMIP 1-1) or 12 (DCMIP 1-2)");
+  if (!s->have_latlon || s->hv_hyam.empty()) return fail("tse_dcmip_init: needs spherep lat/lon and hyam/hybm at tse_init");
+  s->test_case = test_case;
+  DcmipHostTables t;
+  dcmip_fill_tables(test_case, s->hv_hyai.data(), s->hv_hybi.data(), s->hv_hyam.data(), s->hv_hybm.data(), s->ps0, t);
+  auto up = [&](const double* h, const double** d) -> int {
+    std::vector<double> v(h, h + NLEV);
+    double* p = nullptr;
+    if (upload(s, &p, v)) return 1;
+    *d = p;
+    return 0;
+  };
+  if (up(t.zm, &s->dcmip.zm) || up(t.dp_ref, &s->dcmip.dp_ref) || up(t.vm, &s->dcmip.vm) || up(t.vi, &s->dcmip.vi) ||
+      up(t.dp_ic, &s->dcmip.dp_ic))
+    return 1;
+  s->slot_buf[1] = 0; s->slot_buf[2] = 1;
+  s->slot_pending[1] = s->slot_pending[2] = 0;
+  k_dcmip_ic<<<s->ngroups * NKC, 256, 0, s->stream>>>(test_case, s->nelem, s->Q, s->d_lon, s->d_lat, s->dcmip, s->qbuf[0], s->qbuf[1]);
+  ++s->launches;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// prim_run_subcycle (prim_driver_mod.F90:701-854) with prim_step (:858-943) and prim_advance_exp (prim_advance_mod.F90:70-152)
+int tse_prim_run_subcycle(tse_handle s, double tstep, int* nstep_io) {
+  if (!s->test_case) return fail("tse_prim_run_subcycle: call tse_dcmip_init first");
+  int nstep = *nstep_io;
+  const int rsplit = s->cfg.rsplit > 0 ? s->cfg.rsplit : 1, qsplit = s->cfg.qsplit > 0 ? s->cfg.qsplit : 1;
+  if (qsplit != 1) return fail("tse_prim_run_subcycle: qsplit=%d not supported by the device driver", qsplit);
+  ScopedTimer tm(s, "prim_run");
+  for (int r = 1; r <= rsplit; ++r) {
+    if (r > 1) ++nstep;  // TimeLevel_update
+    {
+      ScopedTimer t2(s, "prim_advance_exp");
+      // v(n0) was evaluated by the previous step (time 0 for the first one): winds are lagged one step
+      const double t_prev = (nstep > 0 ? nstep - 1 : 0) * tstep, t_now = nstep * tstep;
+      k_dcmip_wind<<<s->ngroups * NKC, 256, 0, s->stream>>>(s->test_case, t_prev, t_now, s->nelem, s->d_lon, s->d_lat, s->dcmip, s->vn0,
+                                                            s->dp, s->eta_dot, s->omega_p);
+      ++s->launches;
+      CU(cudaGetLastError());
+    }
+    if (tse_advec_tracers_remap_rk2(s, tstep * qsplit, nstep)) return 1;
+  }
+  const int np1_qdp = ((nstep / qsplit) % 2 == 0) ? 2 : 1;
+  if (tse_vertical_remap(s, tstep * qsplit * rsplit, 0, np1_qdp)) return 1;
+  ++nstep;
+  *nstep_io = nstep;
+  return 0;
+}
+
+// global tracer mass sum_e sum_k sum_ij spheremp*Qdp with an order-independent fixed-point sum
+// (the repro_sum idea, repro_sum_mod.F90:216-628: bitwise identical for any element order / GPU count)
+int tse_diag_mass(tse_handle s, int tl, double* mass) {
+  if (check_tl(tl)) return 1;
+  const DssView v = view(s, s->slot_buf[tl], s->slot_pending[tl]);
+  const int Q = s->Q;
+  CU(cudaMemsetAsync(s->d_maxbits, 0, sizeof(unsigned long long) * Q, s->stream));
+  CU(cudaMemsetAsync(s->d_acc, 0, sizeof(long long) * 2 * Q, s->stream));
+  k_mass_max<<<plane_grid(s), GPL * QPB, 0, s->stream>>>(s->geo, v, s->d_maxbits);
+  ++s->launches;
+  std::vector<unsigned long long> mb(Q);
+  CU(cudaMemcpyAsync(mb.data(), s->d_maxbits, sizeof(unsigned long long) * Q, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  std::vector<int> shift(Q);
+  for (int q = 0; q < Q; ++q) {
+    double mx;
+    std::memcpy(&mx, &mb[q], 8);
+    shift[q] = 37 - (mx > 0 ? std::ilogb(mx) : 0);  // |J|*2^shift < 2^38; up to 2^23 planes per tracer sum below 2^61
+  }
+  CU(cudaMemcpyAsync(s->d_shift, shift.data(), sizeof(int) * Q, cudaMemcpyHostToDevice, s->stream));
+  k_mass_fixed<<<plane_grid(s), GPL * QPB, 0, s->stream>>>(s->geo, v, s->d_shift, s->d_acc);
+  ++s->launches;
+  std::vector<long long> acc(2 * Q);
+  CU(cudaMemcpyAsync(acc.data(), s->d_acc, sizeof(long long) * 2 * Q, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  for (int q = 0; q < Q; ++q) {
+    const long double tot = (long double)acc[2 * q] + std::ldexp((long double)acc[2 * q + 1], -40);
+    mass[q] = (double)std::ldexp(tot, -shift[q]);
+  }
+  return 0;
+}
 int tse_diag_qminmax(tse_handle, int, double*, double*) { return fail("tse_diag_qminmax: not in this build yet"); }
 
 double tse_timer_ms(tse_handle s, const char* name) {
+  resolve_timers(s);
   auto it = s->timers.find(name);
   return it == s->timers.end() ? -1.0 : it->second;
 }
 long long tse_launch_count(tse_handle s) { return s->launches; }
+long long tse_stage_launch_count(tse_handle s) { return s->stage_launches; }
+
+int tse_mark(tse_handle s, int slot) {
+  if (slot < 0 || slot >= 16) return fail("tse_mark: slot %d", slot);
+  if (!s->marks[slot]) CU(cudaEventCreate(&s->marks[slot]));
+  CU(cudaEventRecord(s->marks[slot], s->stream));
+  return 0;
+}
+double tse_mark_elapsed_ms(tse_handle s, int a, int b) {
+  if (a < 0 || a >= 16 || b < 0 || b >= 16 || !s->marks[a] || !s->marks[b]) return -1.0;
+  if (cudaEventSynchronize(s->marks[b]) != cudaSuccess) return -1.0;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, s->marks[a], s->marks[b]) != cudaSuccess) return -1.0;
+  return ms;
+}
+int tse_timer_reset(tse_handle s) {
+  resolve_timers(s);
+  s->timers.clear();
+  return 0;
+}
+int tse_get_wind(tse_handle s, double* vn0, long long s_vn0, double* dp, long long s_dp) {
+  if (level_copy(s, s->vn0, vn0, s_vn0, 2, NLEV, 0)) return 1;
+  return level_copy(s, s->dp, dp, s_dp, 1, NLEV, 0);
+}
 long long tse_device_bytes(tse_handle s) { return s->dev_bytes; }
 
 }  // extern "C"

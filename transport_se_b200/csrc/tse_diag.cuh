@@ -1,0 +1,54 @@
+// Diagnostics: order-independent global tracer mass (the fixed-point idea of repro_sum, reference
+// src/repro_sum_mod.F90:216-628, applied to the "Q mass" sum of prim_state_mod.F90:352-385).
+// Each plane's J = sum_ij spheremp*Qdp is split into two int64 limbs relative to the global max exponent;
+// integer adds commute, so the result is bitwise identical for any element order, block schedule or GPU count.
+#pragma once
+#include "tse_kernels.cuh"
+
+namespace tse {
+
+__device__ __forceinline__ double plane_mass(const Geo& G, const DssView& in, const ThreadPlane& t) {
+  double v[16];
+  in.load(G, t.e, t.q, t.k, v);
+  const double* sp = G.spheremp + (size_t)t.e * 16;
+  double J = 0.0;
+  TSE_UNROLL
+  for (int n = 0; n < 16; ++n) J = fma(sp[n], v[n], J);
+  return J;
+}
+
+__global__ void __launch_bounds__(GPL* QPB) k_mass_max(Geo G, DssView in, unsigned long long* __restrict__ maxbits) {
+  const ThreadPlane t = thread_plane(G, in.Q);
+  unsigned long long b = 0;
+  if (t.valid) b = (unsigned long long)__double_as_longlong(fabs(plane_mass(G, in, t)));
+  TSE_UNROLL
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long x = __shfl_xor_sync(0xffffffffu, b, o);
+    b = x > b ? x : b;
+  }
+  const int q = blockIdx.y * QPB + threadIdx.x / GPL;  // uniform per warp
+  if ((threadIdx.x & 31) == 0 && q < in.Q) atomicMax(maxbits + q, b);
+}
+
+__global__ void __launch_bounds__(GPL* QPB) k_mass_fixed(Geo G, DssView in, const int* __restrict__ shift, long long* __restrict__ acc) {
+  const ThreadPlane t = thread_plane(G, in.Q);
+  const int q = blockIdx.y * QPB + threadIdx.x / GPL;
+  long long hi = 0, lo = 0;
+  if (t.valid) {
+    const double x = scalbn(plane_mass(G, in, t), shift[q]);
+    const double xi = trunc(x);
+    hi = (long long)xi;
+    lo = (long long)trunc(scalbn(x - xi, 40));
+  }
+  TSE_UNROLL
+  for (int o = 16; o > 0; o >>= 1) {
+    hi += __shfl_xor_sync(0xffffffffu, hi, o);
+    lo += __shfl_xor_sync(0xffffffffu, lo, o);
+  }
+  if ((threadIdx.x & 31) == 0 && q < in.Q) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(acc + 2 * q), (unsigned long long)hi);
+    atomicAdd(reinterpret_cast<unsigned long long*>(acc + 2 * q + 1), (unsigned long long)lo);
+  }
+}
+
+}  // namespace tse
