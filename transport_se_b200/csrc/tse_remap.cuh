@@ -56,8 +56,11 @@ __global__ void __launch_bounds__(RM_THREADS, 1) k_vertical_remap(RemapArgs a) {
     s_dpo[k + 1][n] = d;
     neg |= (d < 0.0);
   }
-  if (neg) *a.error_flag = 1;
-  __syncthreads();
+  // the reference aborts here (prim_advection_mod.F90:1319-1324); the grid search below needs monotone pressures
+  if (__syncthreads_or(neg)) {
+    if (threadIdx.x == 0) *a.error_flag = 1;
+    return;
+  }
   if (kl == 0) {
     double s = 0.0;
     for (int k = 1; k <= NLEV; ++k) s += s_dpo[k + 1][n];  // sum(dp3d,3)
