@@ -14,6 +14,7 @@
 #include "tse.h"
 #include "tse_kernels.cuh"
 #include "tse_remap.cuh"
+#include "tse_tile.cuh"
 #include "tse_dcmip.cuh"
 #include "tse_diag.cuh"
 
@@ -84,6 +85,10 @@ struct tse_state {
   std::vector<double> hv_hyai, hv_hybi, hv_hyam, hv_hybm;
   double ps0 = 0;
   bool have_latlon = false;
+  // tiled kernels
+  TileTables tiles{};
+  int tile_smem = 0;
+  bool use_tiled = true;
   // diagnostics
   unsigned long long* d_maxbits = nullptr;
   long long* d_acc = nullptr;
@@ -147,6 +152,26 @@ int pick_buffer(const tse_state* s, std::initializer_list<int> protect) {
   return -1;
 }
 
+TileArgs tile_args(const tse_state* s) {
+  TileArgs a{};
+  a.vn0 = s->vn0; a.dp = s->dp; a.divdp = s->divdp; a.divdp_proj = s->divdp_proj;
+  a.dp0 = s->d_dp0;
+  a.qmin = s->qmin; a.qmax = s->qmax; a.qmin_loc = s->qmin_loc; a.qmax_loc = s->qmax_loc;
+  a.Q = s->Q;
+  a.rkstage = 3.0;
+  return a;
+}
+template <int OP>
+void launch_tile(tse_state* s, const TileArgs& a) {
+  k_tile<OP><<<s->ngroups * NKC, TT, s->tile_smem, s->stream>>>(s->geo, s->dvv, s->tiles, a);
+  ++s->launches;
+}
+void launch_nbr_minmax(tse_state* s) {
+  const size_t total = (size_t)s->ngroups * NKC * s->Q * GPL;
+  k_nbr_minmax<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(s->geo, s->Q, s->qmin_loc, s->qmax_loc, nullptr, s->qmin, s->qmax);
+  ++s->launches;
+}
+
 int check_tl(int tl) { return (tl == 1 || tl == 2) ? 0 : fail("time level %d out of range (1|2)", tl); }
 
 int resolve_slot(tse_state* s, int tl) {
@@ -154,8 +179,14 @@ int resolve_slot(tse_state* s, int tl) {
   const int other = s->slot_buf[3 - tl];
   const int in = s->slot_buf[tl];
   const int out = pick_buffer(s, {in, other});
-  k_resolve<<<plane_grid(s), GPL * QPB, 0, s->stream>>>(s->geo, view(s, in, 1), s->qbuf[out]);
-  ++s->launches;
+  if (s->use_tiled) {
+    TileArgs a = tile_args(s);
+    a.src[0] = s->qbuf[in]; a.pending[0] = 1; a.out = s->qbuf[out];
+    launch_tile<OP_RESOLVE>(s, a);
+  } else {
+    k_resolve<<<plane_grid(s), GPL * QPB, 0, s->stream>>>(s->geo, view(s, in, 1), s->qbuf[out]);
+    ++s->launches;
+  }
   CU(cudaGetLastError());
   s->slot_buf[tl] = out;
   s->slot_pending[tl] = 0;
@@ -206,6 +237,62 @@ int check_device_error(tse_state* s) {
   CU(cudaStreamSynchronize(s->stream));
   if (flag) return fail("vertical_remap: negative layer thickness.  timestep or remap time too large");  // prim_advection_mod.F90:1323
   return 0;
+}
+
+
+
+int dss_level_field(tse_state* s, int DSSopt) {
+  // DSS of the extra level field (prim_advection_mod.F90:913-919, 943-958)
+  double** f = DSSopt == TSE_DSS_ETA ? &s->eta_dot : DSSopt == TSE_DSS_OMEGA ? &s->omega_p : DSSopt == TSE_DSS_DIV_VDP_AVE ? &s->divdp_proj : nullptr;
+  if (DSSopt != TSE_DSS_NO_VAR && !f) return fail("tse_euler_step: DSSopt=%d", DSSopt);
+  if (f) {
+    k_dss_level<<<level_blocks(s), 128, 0, s->stream>>>(s->geo, *f, nullptr, s->lev_tmp);
+    ++s->launches;
+    CU(cudaGetLastError());
+    std::swap(*f, s->lev_tmp);
+  }
+  return 0;
+}
+
+int euler_step_tiled(tse_state* s, int np1_qdp, int n0_qdp, double dt, int DSSopt, int rhs_multiplier) {
+  const int in = s->slot_buf[n0_qdp], in_pending = s->slot_pending[n0_qdp];
+  const int other = (np1_qdp == n0_qdp) ? s->slot_buf[3 - np1_qdp] : -1;  // the untouched time level
+  TileArgs a = tile_args(s);
+  a.rhs_mult_dt = rhs_multiplier * dt;
+  a.dt = dt;
+  a.visc_coef = -3.0 * dt * s->cfg.nu_q;  // rhs_viss = 3 (prim_advection_mod.F90:797,823)
+  int tmp = -1;
+  if (rhs_multiplier == 0) {
+    a.src[0] = s->qbuf[in]; a.pending[0] = in_pending;
+    launch_tile<OP_MINMAX>(s, a);
+    launch_nbr_minmax(s);
+  } else if (rhs_multiplier == 2) {
+    tmp = pick_buffer(s, {in, other});
+    if (tmp < 0) return fail("tse_euler_step: no free tracer buffer");
+    a.src[0] = s->qbuf[in]; a.pending[0] = in_pending; a.out = s->qbuf[tmp];
+    launch_tile<OP_BIHARM_PRE>(s, a);
+    launch_nbr_minmax(s);
+  }
+  const int outb = pick_buffer(s, {in, other, tmp});
+  if (outb < 0) return fail("tse_euler_step: no free tracer buffer");
+  a.out = s->qbuf[outb];
+  {
+    ScopedTimer tk(s, "k_euler_stage");
+    if (rhs_multiplier == 2) {
+      a.src[0] = s->qbuf[tmp]; a.pending[0] = 1;
+      a.src[1] = s->qbuf[in]; a.pending[1] = in_pending;
+      launch_tile<OP_STAGE3>(s, a);
+    } else {
+      a.src[0] = s->qbuf[in]; a.pending[0] = in_pending;
+      if (rhs_multiplier == 0) launch_tile<OP_STAGE1>(s, a);
+      else launch_tile<OP_STAGE2>(s, a);
+    }
+    ++s->stage_launches;
+  }
+  CU(cudaGetLastError());
+  s->slot_buf[np1_qdp] = outb;
+  s->slot_pending[np1_qdp] = 1;
+  return dss_level_field(s, DSSopt);
 }
 
 }  // namespace
@@ -331,6 +418,43 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
   if (conn->ncycles > 0) return fail("tse_init: multi-rank connectivity needs tse_comm_init (not in this build yet)");
   int *d_gsrc, *d_nbr8;
   if (upload(s, &d_gsrc, gsrc) || upload(s, &d_nbr8, nbr8)) return 1;
+  {
+    // group-local view of the gather table: sources inside the 16-element group are read from the shared-memory tile,
+    // everything else (other groups, other GPUs) goes through a per-group halo list
+    std::vector<int> gsrc_t((size_t)s->npad * NSLOT, -1), halo_off(s->ngroups + 1, 0), halo_src;
+    int hmax = 1;
+    for (int g = 0; g < s->ngroups; ++g) {
+      std::vector<int> ext;
+      for (int el = 0; el < GE; ++el)
+        for (int x = 0; x < NSLOT; ++x) {
+          const int code = gsrc[((size_t)g * GE + el) * NSLOT + x];
+          if (code == -1) continue;
+          if (code >= 0 && (code >> 4) / GE == g) continue;
+          ext.push_back(code);
+        }
+      std::sort(ext.begin(), ext.end());
+      ext.erase(std::unique(ext.begin(), ext.end()), ext.end());
+      for (int el = 0; el < GE; ++el)
+        for (int x = 0; x < NSLOT; ++x) {
+          const size_t i = ((size_t)g * GE + el) * NSLOT + x;
+          const int code = gsrc[i];
+          if (code == -1) continue;
+          if (code >= 0 && (code >> 4) / GE == g) gsrc_t[i] = (((code >> 4) % GE) << 4) | (code & 15);
+          else gsrc_t[i] = 256 + (int)(std::lower_bound(ext.begin(), ext.end(), code) - ext.begin());
+        }
+      halo_off[g + 1] = halo_off[g] + (int)ext.size();
+      halo_src.insert(halo_src.end(), ext.begin(), ext.end());
+      hmax = std::max(hmax, (int)ext.size());
+    }
+    if (halo_src.empty()) halo_src.push_back(-1);
+    int *d_a, *d_b, *d_c;
+    if (upload(s, &d_a, gsrc_t) || upload(s, &d_b, halo_off) || upload(s, &d_c, halo_src)) return 1;
+    s->tiles.gsrc_t = d_a; s->tiles.halo_off = d_b; s->tiles.halo_src = d_c; s->tiles.hmax = hmax;
+    s->tile_smem = tile_smem_bytes(hmax);
+    if (s->tile_smem > 227 * 1024) return fail("tse_init: halo of %d nodes per group does not fit in shared memory", hmax);
+    const char* env = getenv("TSE_KERNELS");
+    s->use_tiled = !(env && std::string(env) == "v1");
+  }
   s->geo.spheremp = d_sp; s->geo.rspheremp = d_rsp; s->geo.rmp = d_rmp; s->geo.rmr = d_rmr; s->geo.mD = d_mD; s->geo.T = d_T;
   s->geo.gsrc = d_gsrc; s->geo.nbr8 = d_nbr8; s->geo.nelem = ne; s->geo.ngroups = s->ngroups;
 
@@ -384,6 +508,13 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
     if (dalloc(s, &s->stage, s->stage_doubles)) return 1;
   }
   CU(cudaFuncSetAttribute(k_vertical_remap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RM_SMEM));
+  CU(cudaFuncSetAttribute(k_tile<OP_MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->tile_smem));
+  CU(cudaFuncSetAttribute(k_tile<OP_STAGE1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->tile_smem));
+  CU(cudaFuncSetAttribute(k_tile<OP_STAGE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->tile_smem));
+  CU(cudaFuncSetAttribute(k_tile<OP_STAGE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->tile_smem));
+  CU(cudaFuncSetAttribute(k_tile<OP_BIHARM_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->tile_smem));
+  CU(cudaFuncSetAttribute(k_tile<OP_TIME_AVG>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->tile_smem));
+  CU(cudaFuncSetAttribute(k_tile<OP_RESOLVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->tile_smem));
   CU(cudaStreamSynchronize(s->stream));
   *out = s;
   return 0;
@@ -522,6 +653,7 @@ int tse_euler_step(tse_handle s, int np1_qdp, int n0_qdp, double dt, int DSSopt,
   if (check_tl(np1_qdp) || check_tl(n0_qdp)) return 1;
   ScopedTimer tm(s, "euler_step");
   if (rhs_multiplier < 0 || rhs_multiplier > 2) return fail("tse_euler_step: rhs_multiplier=%d", rhs_multiplier);
+  if (s->use_tiled) return euler_step_tiled(s, np1_qdp, n0_qdp, dt, DSSopt, rhs_multiplier);
   const int in = s->slot_buf[n0_qdp], in_pending = s->slot_pending[n0_qdp];
   const dim3 grid = plane_grid(s);
   const int threads = GPL * QPB;
@@ -581,9 +713,17 @@ int tse_qdp_time_avg(tse_handle s, int rkstage, int n0_qdp, int np1_qdp) {
   if (resolve_slot(s, n0_qdp)) return 1;
   const int in = s->slot_buf[np1_qdp], q0 = s->slot_buf[n0_qdp];
   const int outb = pick_buffer(s, {in, q0});
+  if (s->use_tiled) {
+    TileArgs a = tile_args(s);
+    a.src[0] = s->qbuf[q0]; a.pending[0] = 0;
+    a.src[1] = s->qbuf[in]; a.pending[1] = s->slot_pending[np1_qdp];
+    a.out = s->qbuf[outb];
+    a.rkstage = (double)rkstage;
+    launch_tile<OP_TIME_AVG>(s, a);
+  } else
   k_time_avg<<<plane_grid(s), GPL * QPB, 0, s->stream>>>(s->geo, view(s, in, s->slot_pending[np1_qdp]), s->qbuf[q0], (double)rkstage,
                                                          s->qbuf[outb]);
-  ++s->launches;
+  if (!s->use_tiled) ++s->launches;
   CU(cudaGetLastError());
   s->slot_buf[np1_qdp] = outb;
   s->slot_pending[np1_qdp] = 0;
