@@ -44,6 +44,7 @@ def build_cuda(force=False, verbose=False):
                "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
         if verbose:
             cmd += ["-Xptxas", "-v"]
+        cmd += os.environ.get("TSE_NVCC_FLAGS", "").split()
         cmd += ["-o", out] + srcs + ["-lnccl"]
         log = _run(cmd)
         if verbose:

@@ -163,7 +163,7 @@ TileArgs tile_args(const tse_state* s) {
 }
 template <int OP>
 void launch_tile(tse_state* s, const TileArgs& a) {
-  k_tile<OP><<<s->ngroups * NKC, TT, s->tile_smem, s->stream>>>(s->geo, s->dvv, s->tiles, a);
+  k_tile<OP><<<s->ngroups * NKC, TT, tile_smem_bytes(OP, s->tiles.hmax), s->stream>>>(s->geo, s->dvv, s->tiles, a);
   ++s->launches;
 }
 void launch_nbr_minmax(tse_state* s) {
@@ -450,7 +450,7 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
     int *d_a, *d_b, *d_c;
     if (upload(s, &d_a, gsrc_t) || upload(s, &d_b, halo_off) || upload(s, &d_c, halo_src)) return 1;
     s->tiles.gsrc_t = d_a; s->tiles.halo_off = d_b; s->tiles.halo_src = d_c; s->tiles.hmax = hmax;
-    s->tile_smem = tile_smem_bytes(hmax);
+    s->tile_smem = tile_smem_bytes(OP_STAGE2, hmax);
     if (s->tile_smem > 227 * 1024) return fail("tse_init: halo of %d nodes per group does not fit in shared memory", hmax);
     const char* env = getenv("TSE_KERNELS");
     s->use_tiled = !(env && std::string(env) == "v1");
@@ -508,13 +508,13 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
     if (dalloc(s, &s->stage, s->stage_doubles)) return 1;
   }
   CU(cudaFuncSetAttribute(k_vertical_remap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RM_SMEM));
-  CU(cudaFuncSetAttribute(k_tile<OP_MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->tile_smem));
-  CU(cudaFuncSetAttribute(k_tile<OP_STAGE1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->tile_smem));
-  CU(cudaFuncSetAttribute(k_tile<OP_STAGE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->tile_smem));
-  CU(cudaFuncSetAttribute(k_tile<OP_STAGE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->tile_smem));
-  CU(cudaFuncSetAttribute(k_tile<OP_BIHARM_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->tile_smem));
-  CU(cudaFuncSetAttribute(k_tile<OP_TIME_AVG>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->tile_smem));
-  CU(cudaFuncSetAttribute(k_tile<OP_RESOLVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->tile_smem));
+  CU(cudaFuncSetAttribute(k_tile<OP_MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_MINMAX, s->tiles.hmax)));
+  CU(cudaFuncSetAttribute(k_tile<OP_STAGE1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_STAGE1, s->tiles.hmax)));
+  CU(cudaFuncSetAttribute(k_tile<OP_STAGE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_STAGE2, s->tiles.hmax)));
+  CU(cudaFuncSetAttribute(k_tile<OP_STAGE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_STAGE3, s->tiles.hmax)));
+  CU(cudaFuncSetAttribute(k_tile<OP_BIHARM_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_BIHARM_PRE, s->tiles.hmax)));
+  CU(cudaFuncSetAttribute(k_tile<OP_TIME_AVG>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_TIME_AVG, s->tiles.hmax)));
+  CU(cudaFuncSetAttribute(k_tile<OP_RESOLVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_RESOLVE, s->tiles.hmax)));
   CU(cudaStreamSynchronize(s->stream));
   *out = s;
   return 0;

@@ -1,17 +1,22 @@
 // Tiled tracer-field kernels (sm_100a): the production versions of the plane-per-thread kernels in tse_kernels.cuh.
 //
-// CTA = (group of 16 elements, chunk of 4 levels); it walks all tracers, QI=2 at a time, through a double-buffered
-// cp.async pipeline.  For each step the 16 KB tile [q][el][kk][16] (contiguous in HBM) is copied with coalesced 16-byte
-// cp.async into shared memory, XOR-swizzled per 128-byte plane so that a thread can read "its" plane with conflict-free
-// 128-bit loads.  One thread owns one plane: all 4x4 contractions, the limiter and the extrema are register-only.
+// CTA = (group of 16 elements, chunk of 4 levels), QI*64 threads; it walks all tracers, QI at a time.  For each step the
+// QI*8 KB tile [q][el][kk][16] (contiguous in HBM) is copied with coalesced 16-byte cp.async into shared memory (IN buffer),
+// XOR-swizzled per 128-byte plane so that a thread can read "its" plane with conflict-free 128-bit loads.  One thread owns
+// one plane: all 4x4 contractions, the limiter and the extrema are register-only.  As soon as every thread has pulled its
+// plane (and its DSS neighbours) into registers the next tile is prefetched into the same IN buffer, overlapping the whole
+// compute phase; results are staged in a second (OUT) buffer and written back with coalesced 16-byte stores.
+//
+// A warp holds 8/QI elements x 4 levels x QI tracers, so that the data-dependent limiter loop diverges as little as possible
+// (the behaviour of a plane is mostly a property of its element).
 //
 // DSS (edgeVpack / bndry_exchangeV / edgeVunpack, edge_mod.F90:366-742) is fused into the load of the consumer: a field is
 // stored "pre-DSS" (spheremp-weighted); neighbours inside the group are read straight from the tile in shared memory,
-// neighbours outside the group (the patch perimeter, ~68 nodes for a 4x4 patch) are fetched by 8-byte cp.async into a halo
-// array in the same pipeline stage, and the sum runs in the reference's unpack order.  The rspheremp factor of the DSS is
-// folded into the per-level package (E1, U, rdp below), computed once per CTA and reused for all tracers.
+// neighbours outside the group (the patch perimeter, 68 nodes for a 4x4 patch) are fetched by 8-byte cp.async into a halo
+// array next to the tile, and the sum runs in the reference's unpack order.  The rspheremp factor of the DSS is folded into
+// the per-level package below, computed once per CTA and reused for all tracers.
 //
-// Per-(element, level) package (registers/shared memory, tracer independent), with rX = rspheremp if the input is pre-DSS else 1:
+// Per-(element, level) package (shared memory, tracer independent), with rX = rspheremp if the input is pre-DSS else 1:
 //   dp_s = dp - rhs_mult*dt*divdp_proj, Vstar = vn0/dp_s, dp_star = dp_s - dt*divdp        (prim_advection_mod.F90:753,847-864)
 //   U_c  = rX * metdet*(Dinv(c,1)*Vstar1 + Dinv(c,2)*Vstar2)      gv_c = U_c * S       (S = raw DSS sum)
 //   E1   = spheremp*rX, E2 = dt*spheremp*rmetdet*rrearth          y = spheremp*Qtens = E1*S - E2*div
@@ -22,9 +27,17 @@
 
 namespace tse {
 
-constexpr int QI = 2;                  // tracers per pipeline step
-constexpr int TT = QI * GPL;           // 128 threads
-constexpr int TILE_BYTES = TT * 128;   // 16 KB
+#ifndef TSE_QI
+#define TSE_QI 2
+#endif
+#ifndef TSE_MINB
+#define TSE_MINB 2
+#endif
+constexpr int QI = TSE_QI;             // tracers per pipeline step
+constexpr int TT = QI * GPL;           // threads per CTA (256 for QI = 4)
+constexpr int TILE_BYTES = TT * 128;   // 32 KB for QI = 4
+constexpr int HPRE = 512 / TT;         // halo entries per thread resolved before the tracer loop (covers hmax <= 128)
+constexpr int EPW = 8 / QI;            // elements per warp
 
 enum TileOp { OP_MINMAX = 0, OP_STAGE1, OP_STAGE2, OP_STAGE3, OP_BIHARM_PRE, OP_TIME_AVG, OP_RESOLVE };
 
@@ -36,7 +49,7 @@ struct TileTables {
 };
 
 struct TileArgs {
-  const double* src[2];    // input fields: [0] main (Qdp), [1] second (STAGE3: qtens is src[0], Qdp is src[1]; TIME_AVG: q0 is src[0])
+  const double* src[2];    // input fields.  STAGE3: [0] = qtens, [1] = Qdp;  TIME_AVG: [0] = Qdp(n0), [1] = Qdp(np1)
   int pending[2];
   const double* ghost[2];
   double* out;
@@ -47,12 +60,27 @@ struct TileArgs {
   int Q;
 };
 
-__host__ __device__ inline int tile_stage_bytes(int hmax) { return TILE_BYTES + QI * hmax * KC * 8 + 16; }
 constexpr int PP_BYTES = GPL * 128;  // per-plane package field (8 KB)
 constexpr int EL_BYTES = GE * 128;   // per-element package field (2 KB)
-enum { PP_U1 = 0, PP_U2, PP_CL, PP_RDP, NPP };
-enum { EL_E1 = 0, EL_E2, EL_RSPH, EL_T11, EL_T12, EL_T22, NEL };
-__host__ __device__ inline int tile_smem_bytes(int hmax) { return 2 * tile_stage_bytes(hmax) + NPP * PP_BYTES + NEL * EL_BYTES; }
+
+// which package fields an op keeps in shared memory
+struct TileCfg {
+  int npp, nel, has_out;
+  int U1, U2, CL, RDP;            // per-plane field slots
+  int E1, E2, RSPH, T11, T12, T22;  // per-element field slots
+};
+__host__ __device__ constexpr TileCfg tile_cfg(int op) {
+  return op == OP_STAGE1 ? TileCfg{3, 2, 1, 0, 1, 2, -1, 0, 1, -1, -1, -1, -1}
+       : op == OP_STAGE2 ? TileCfg{4, 2, 1, 0, 1, 2, 3, 0, 1, -1, -1, -1, -1}
+       : op == OP_STAGE3 ? TileCfg{3, 6, 1, 0, 1, 2, -1, 0, 1, 2, 3, 4, 5}
+       : op == OP_MINMAX ? TileCfg{1, 0, 0, -1, -1, -1, 0, -1, -1, -1, -1, -1, -1}
+       : op == OP_BIHARM_PRE ? TileCfg{1, 3, 1, -1, -1, -1, 0, -1, -1, -1, 0, 1, 2}
+                             : TileCfg{0, 1, 1, -1, -1, -1, -1, -1, -1, 0, -1, -1, -1};
+}
+__host__ __device__ constexpr int tile_in_bytes(int hmax) { return TILE_BYTES + QI * hmax * KC * 8 + 16; }
+__host__ __device__ constexpr int tile_smem_bytes(int op, int hmax) {
+  return tile_in_bytes(hmax) + (tile_cfg(op).has_out ? TILE_BYTES : 0) + tile_cfg(op).npp * PP_BYTES + tile_cfg(op).nel * EL_BYTES;
+}
 
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
@@ -61,94 +89,136 @@ __device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
 
 __device__ __forceinline__ double2 lds128(const unsigned char* base, int off) { return *reinterpret_cast<const double2*>(base + off); }
 __device__ __forceinline__ double lds64(const unsigned char* base, int off) { return *reinterpret_cast<const double*>(base + off); }
 
-// per-plane package field: 16-byte unit index c*64 + pl
-__device__ __forceinline__ void ld_pp(const unsigned char* f, int pl, double (&v)[16]) {
-  TSE_UNROLL
-  for (int c = 0; c < 8; ++c) {
-    const double2 t = lds128(f, (c * GPL + pl) * 16);
-    v[2 * c] = t.x;
-    v[2 * c + 1] = t.y;
-  }
-}
-// per-element package field: 16-byte unit index c*16 + el
-__device__ __forceinline__ void ld_el(const unsigned char* f, int el, double (&v)[16]) {
-  TSE_UNROLL
-  for (int c = 0; c < 8; ++c) {
-    const double2 t = lds128(f, (c * GE + el) * 16);
-    v[2 * c] = t.x;
-    v[2 * c + 1] = t.y;
-  }
+// volatile shared-memory load: keeps the limiter's c out of registers (re-read from the package each pass)
+__device__ __forceinline__ double2 lds128v(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
 }
 
 // limiter_optim_iter_full (prim_advection_mod.F90:976-1094) on y = c*x (mass contributions) instead of x:
 // x > maxp  <=>  y > maxp*c ; addmass += (x-maxp)*c = y - maxp*c ; x += inc  <=>  y += inc*c ; result ptens*sphweights = y.
-__device__ __forceinline__ void limiter_y(double (&y)[16], const double (&c)[16], double sumc, double& minp, double& maxp) {
+// c is read from the per-plane package in shared memory (cbase = shared address of chunk 0 of this plane, chunk stride
+// GPL*16 bytes).  Sums use 4 interleaved partial accumulators (fixed order, identical on every GPU count).
+__device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, double sumc, double& minp, double& maxp) {
   const double tol_limiter = (double)5e-14f;
   if (sumc <= 0.0) return;
-  double mass = 0.0;
-  TSE_UNROLL
-  for (int k1 = 0; k1 < 16; ++k1) mass += y[(k1 >> 2) + 4 * (k1 & 3)];
+  double mass;
+  {
+    double m0 = y[0], m1 = y[1], m2 = y[2], m3 = y[3];
+    TSE_UNROLL
+    for (int n = 4; n < 16; n += 4) {
+      m0 += y[n];
+      m1 += y[n + 1];
+      m2 += y[n + 2];
+      m3 += y[n + 3];
+    }
+    mass = (m0 + m1) + (m2 + m3);
+  }
   if (mass < minp * sumc) minp = mass / sumc;
   if (mass > maxp * sumc) maxp = mass / sumc;
   const double thresh = tol_limiter * fabs(mass);
+#pragma unroll 1
   for (int iter = 1; iter <= NPSQ - 1; ++iter) {
-    double addmass = 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     TSE_UNROLL
-    for (int k1 = 0; k1 < 16; ++k1) {
-      const int n = (k1 >> 2) + 4 * (k1 & 3);
-      const double hi = maxp * c[n], lo = minp * c[n];
-      if (y[n] > hi) {
-        addmass += y[n] - hi;
-        y[n] = hi;
-      }
-      if (y[n] < lo) {
-        addmass -= lo - y[n];
-        y[n] = lo;
+    for (int cc = 0; cc < 8; cc += 2) {
+      const double2 ca = lds128v(cbase + cc * GPL * 16), cb = lds128v(cbase + (cc + 1) * GPL * 16);
+      const double cv[4] = {ca.x, ca.y, cb.x, cb.y};
+      TSE_UNROLL
+      for (int u = 0; u < 4; ++u) {
+        const int n = 2 * cc + u;
+        const double hi = maxp * cv[u], lo = minp * cv[u];
+        const double tcl = fmin(fmax(y[n], lo), hi);
+        const double d = y[n] - tcl;  // (x-maxp)*c above, -(minp-x)*c below, 0 inside
+        y[n] = tcl;
+        if (u == 0) a0 += d;
+        if (u == 1) a1 += d;
+        if (u == 2) a2 += d;
+        if (u == 3) a3 += d;
       }
     }
+    const double addmass = (a0 + a1) + (a2 + a3);
     if (fabs(addmass) <= thresh) break;
-    double weightssum = 0.0;
-    if (addmass > 0.0) {
+    // nodes not at the bound the mass is pushed toward share addmass (same increment of x for all of them)
+    const bool up = addmass > 0.0;
+    const double bnd = up ? maxp : minp;
+    double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+    TSE_UNROLL
+    for (int cc = 0; cc < 8; cc += 2) {
+      const double2 ca = lds128v(cbase + cc * GPL * 16), cb = lds128v(cbase + (cc + 1) * GPL * 16);
+      const int n = 2 * cc;
+      if (up ? (y[n] < bnd * ca.x) : (y[n] > bnd * ca.x)) w0 += ca.x;
+      if (up ? (y[n + 1] < bnd * ca.y) : (y[n + 1] > bnd * ca.y)) w1 += ca.y;
+      if (up ? (y[n + 2] < bnd * cb.x) : (y[n + 2] > bnd * cb.x)) w2 += cb.x;
+      if (up ? (y[n + 3] < bnd * cb.y) : (y[n + 3] > bnd * cb.y)) w3 += cb.y;
+    }
+    const double inc = addmass / ((w0 + w1) + (w2 + w3));
+    TSE_UNROLL
+    for (int cc = 0; cc < 8; ++cc) {
+      const double2 ca = lds128v(cbase + cc * GPL * 16);
+      const int n = 2 * cc;
+      if (up ? (y[n] < bnd * ca.x) : (y[n] > bnd * ca.x)) y[n] = fma(inc, ca.x, y[n]);
+      if (up ? (y[n + 1] < bnd * ca.y) : (y[n + 1] > bnd * ca.y)) y[n + 1] = fma(inc, ca.y, y[n + 1]);
+    }
+  }
+}
+
+// y(a,b) = sum_i Dvv(i,a) g1(i,b) + sum_i Dvv(i,b) g2(a,i) with g_c = U_c*S, evaluated row by row / column pair by column pair
+// so that only S, y and 8 temporaries are live (div_contract needs S, g1, g2 and y at once)
+__device__ __forceinline__ void flux_div(const double (&S)[16], const unsigned char* u1, const unsigned char* u2, int pl, const Dvv& D,
+                                         double (&y)[16]) {
+  TSE_UNROLL
+  for (int b = 0; b < 4; ++b) {
+    const double2 ua = lds128(u1, ((2 * b) * GPL + pl) * 16), ub = lds128(u1, ((2 * b + 1) * GPL + pl) * 16);
+    const double g0 = ua.x * S[4 * b], g1 = ua.y * S[4 * b + 1], g2 = ub.x * S[4 * b + 2], g3 = ub.y * S[4 * b + 3];
+    y[4 * b + 0] = fma(D.d[3 + 0], g3, fma(D.d[2 + 0], g2, fma(D.d[1 + 0], g1, D.d[0 + 0] * g0)));
+    y[4 * b + 1] = fma(D.d[3 + 4], g3, fma(D.d[2 + 4], g2, D.d[0 + 4] * g0));   // Dvv(1,1) = 0
+    y[4 * b + 2] = fma(D.d[3 + 8], g3, fma(D.d[1 + 8], g1, D.d[0 + 8] * g0));   // Dvv(2,2) = 0
+    y[4 * b + 3] = fma(D.d[3 + 12], g3, fma(D.d[2 + 12], g2, fma(D.d[1 + 12], g1, D.d[0 + 12] * g0)));
+  }
+  TSE_UNROLL
+  for (int h = 0; h < 2; ++h) {  // columns a = 2h, 2h+1: nodes a + 4 i live in chunks h + 2 i
+    double ge[4], go[4];
+    TSE_UNROLL
+    for (int i = 0; i < 4; ++i) {
+      const double2 u = lds128(u2, ((h + 2 * i) * GPL + pl) * 16);
+      ge[i] = u.x * S[2 * h + 4 * i];
+      go[i] = u.y * S[2 * h + 1 + 4 * i];
+    }
+    TSE_UNROLL
+    for (int b = 0; b < 4; ++b) {
+      double se = 0.0, so = 0.0;
       TSE_UNROLL
-      for (int k1 = 0; k1 < 16; ++k1) {
-        const int n = (k1 >> 2) + 4 * (k1 & 3);
-        if (y[n] < maxp * c[n]) weightssum += c[n];
+      for (int i = 0; i < 4; ++i) {
+        if (!(i == b && (b == 1 || b == 2))) {
+          se = fma(D.d[i + 4 * b], ge[i], se);
+          so = fma(D.d[i + 4 * b], go[i], so);
+        }
       }
-      const double inc = addmass / weightssum;
-      TSE_UNROLL
-      for (int n = 0; n < 16; ++n)
-        if (y[n] < maxp * c[n]) y[n] = fma(inc, c[n], y[n]);
-    } else {
-      TSE_UNROLL
-      for (int k1 = 0; k1 < 16; ++k1) {
-        const int n = (k1 >> 2) + 4 * (k1 & 3);
-        if (y[n] > minp * c[n]) weightssum += c[n];
-      }
-      const double inc = addmass / weightssum;
-      TSE_UNROLL
-      for (int n = 0; n < 16; ++n)
-        if (y[n] > minp * c[n]) y[n] = fma(inc, c[n], y[n]);
+      y[2 * h + 4 * b] += se;
+      y[2 * h + 1 + 4 * b] += so;
     }
   }
 }
 
 // laplace_sphere_wk with the per-element tensor T read from the element-level package
-__device__ __forceinline__ void laplace_wk_el(const double (&s)[16], const Dvv& D, const unsigned char* el_base, int el, double (&lap)[16]) {
+__device__ __forceinline__ void laplace_wk_el(const double (&s)[16], const Dvv& D, const unsigned char* t11, const unsigned char* t12,
+                                              const unsigned char* t22, int el, double (&lap)[16]) {
   double w1[16], w2[16];
   {
     double d1[16], d2[16];
     grad_raw(s, D, d1, d2);
     TSE_UNROLL
     for (int c = 0; c < 8; ++c) {
-      const double2 a = lds128(el_base + EL_T11 * EL_BYTES, (c * GE + el) * 16);
-      const double2 b = lds128(el_base + EL_T12 * EL_BYTES, (c * GE + el) * 16);
-      const double2 cc = lds128(el_base + EL_T22 * EL_BYTES, (c * GE + el) * 16);
+      const double2 a = lds128(t11, (c * GE + el) * 16);
+      const double2 b = lds128(t12, (c * GE + el) * 16);
+      const double2 cc = lds128(t22, (c * GE + el) * 16);
       w1[2 * c] = a.x * d1[2 * c] + b.x * d2[2 * c];
       w2[2 * c] = b.x * d1[2 * c] + cc.x * d2[2 * c];
       w1[2 * c + 1] = a.y * d1[2 * c + 1] + b.y * d2[2 * c + 1];
@@ -171,19 +241,25 @@ __device__ __forceinline__ void laplace_wk_el(const double (&s)[16], const Dvv& 
 }
 
 template <int OP>
-__global__ void __launch_bounds__(TT, 2) k_tile(Geo G, Dvv D, TileTables tb, TileArgs a) {
+__global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables tb, TileArgs a) {
+  constexpr TileCfg cfg = tile_cfg(OP);
   constexpr bool kStage = (OP == OP_STAGE1 || OP == OP_STAGE2 || OP == OP_STAGE3);
   constexpr int NIN = (OP == OP_STAGE3 || OP == OP_TIME_AVG) ? 2 : 1;
-  constexpr bool kHasOut = (OP != OP_MINMAX);
+  constexpr bool kHasOut = cfg.has_out != 0;
   extern __shared__ __align__(16) unsigned char smem[];
-  const int SB = tile_stage_bytes(tb.hmax);
-  unsigned char* const pp = smem + 2 * SB;
-  unsigned char* const elb = pp + NPP * PP_BYTES;
+  const int IN_BYTES = tile_in_bytes(tb.hmax);
+  unsigned char* const outb = smem + IN_BYTES;
+  unsigned char* const pp = outb + (kHasOut ? TILE_BYTES : 0);
+  unsigned char* const elb = pp + cfg.npp * PP_BYTES;
   const int ZERO_OFF = TILE_BYTES + QI * tb.hmax * KC * 8;
 
   const int t = threadIdx.x;
   const int g = blockIdx.x / NKC, kc = blockIdx.x % NKC;
-  const int qi = t / GPL, pl = t % GPL, el = pl / KC, kk = pl % KC;
+  // warp = 2 elements x 4 levels x 4 tracers
+  const int w = t >> 5, lane = t & 31;
+  const int kk = lane & 3, el = EPW * w + ((lane >> 2) % EPW), qi = lane / (4 * EPW);
+  const int pl = el * KC + kk;   // plane within one tracer's tile
+  const int p = qi * GPL + pl;   // plane within the QI-tracer tile
   const int e = g * GE + el, k = kc * KC + kk;
   const bool evalid = e < G.nelem;
   const int Q = a.Q;
@@ -191,8 +267,8 @@ __global__ void __launch_bounds__(TT, 2) k_tile(Geo G, Dvv D, TileTables tb, Til
 
   // ---- level package -------------------------------------------------------------------------------------------
   const bool main_pending = (OP == OP_STAGE3) ? (a.pending[1] != 0) : (a.pending[0] != 0);
-  if (t < 2) *reinterpret_cast<double*>(smem + t * SB + ZERO_OFF) = 0.0;
-  {
+  if (t == 0) *reinterpret_cast<double*>(smem + ZERO_OFF) = 0.0;
+  if (cfg.nel > 0 && t < GE * 8) {
     // element-level fields: thread -> (element t>>3, nodes 2*(t&7), +1)
     const int pe = t >> 3, c = t & 7, ee = g * GE + pe;
     double2 e1 = make_double2(0, 0), e2 = e1, rs = e1, t11 = e1, t12 = e1, t22 = e1;
@@ -204,26 +280,31 @@ __global__ void __launch_bounds__(TT, 2) k_tile(Geo G, Dvv D, TileTables tb, Til
       const double rx0 = main_pending ? rs.x : 1.0, rx1 = main_pending ? rs.y : 1.0;
       e1 = make_double2(sp.x * rx0, sp.y * rx1);
       e2 = make_double2(a.dt * (sp.x * rm.x), a.dt * (sp.y * rm.y));
-      const double* T = G.T + (size_t)ee * 48 + 2 * c;
-      t11 = *reinterpret_cast<const double2*>(T);
-      t12 = *reinterpret_cast<const double2*>(T + 16);
-      t22 = *reinterpret_cast<const double2*>(T + 32);
+      if (cfg.T11 >= 0) {
+        const double* T = G.T + (size_t)ee * 48 + 2 * c;
+        t11 = *reinterpret_cast<const double2*>(T);
+        t12 = *reinterpret_cast<const double2*>(T + 16);
+        t22 = *reinterpret_cast<const double2*>(T + 32);
+      }
     }
     const int off = (c * GE + pe) * 16;
-    *reinterpret_cast<double2*>(elb + EL_E1 * EL_BYTES + off) = e1;
-    *reinterpret_cast<double2*>(elb + EL_E2 * EL_BYTES + off) = e2;
-    *reinterpret_cast<double2*>(elb + EL_RSPH * EL_BYTES + off) = rs;
-    *reinterpret_cast<double2*>(elb + EL_T11 * EL_BYTES + off) = t11;
-    *reinterpret_cast<double2*>(elb + EL_T12 * EL_BYTES + off) = t12;
-    *reinterpret_cast<double2*>(elb + EL_T22 * EL_BYTES + off) = t22;
+    if (cfg.E1 >= 0) *reinterpret_cast<double2*>(elb + cfg.E1 * EL_BYTES + off) = e1;
+    if (cfg.E2 >= 0) *reinterpret_cast<double2*>(elb + cfg.E2 * EL_BYTES + off) = e2;
+    if (cfg.RSPH >= 0) *reinterpret_cast<double2*>(elb + cfg.RSPH * EL_BYTES + off) = rs;
+    if (cfg.T11 >= 0) {
+      *reinterpret_cast<double2*>(elb + cfg.T11 * EL_BYTES + off) = t11;
+      *reinterpret_cast<double2*>(elb + cfg.T12 * EL_BYTES + off) = t12;
+      *reinterpret_cast<double2*>(elb + cfg.T22 * EL_BYTES + off) = t22;
+    }
   }
-  if (kStage || OP == OP_MINMAX || OP == OP_BIHARM_PRE) {
-    // per-plane fields: thread -> (plane t>>1, nodes 8*(t&1) .. +7)
-    const int ppl = t >> 1, half = t & 1;
+  if (cfg.npp > 0) {
+    // per-plane fields: thread -> (plane t / PARTS, 8 / PARTS consecutive 16-byte chunks)
+    constexpr int PARTS = TT / GPL;
+    const int ppl = t / PARTS, part = t % PARTS;
     const int pe = g * GE + ppl / KC, pk = kc * KC + ppl % KC;
     TSE_UNROLL
-    for (int cc = 0; cc < 4; ++cc) {
-      const int c = half * 4 + cc, n = 2 * c;
+    for (int cc = 0; cc < 8 / PARTS; ++cc) {
+      const int c = part * (8 / PARTS) + cc, n = 2 * c;
       double2 u1 = make_double2(0, 0), u2 = u1, cl = make_double2(1, 1), rd = make_double2(1, 1);
       if (pe < G.nelem) {
         const size_t lp = lplane(pe, pk) * 16 + n, gb = (size_t)pe * 16 + n;
@@ -249,15 +330,15 @@ __global__ void __launch_bounds__(TT, 2) k_tile(Geo G, Dvv D, TileTables tb, Til
         }
       }
       const int off = (c * GPL + ppl) * 16;
-      *reinterpret_cast<double2*>(pp + PP_U1 * PP_BYTES + off) = u1;
-      *reinterpret_cast<double2*>(pp + PP_U2 * PP_BYTES + off) = u2;
-      *reinterpret_cast<double2*>(pp + PP_CL * PP_BYTES + off) = cl;
-      *reinterpret_cast<double2*>(pp + PP_RDP * PP_BYTES + off) = rd;
+      if (cfg.U1 >= 0) *reinterpret_cast<double2*>(pp + cfg.U1 * PP_BYTES + off) = u1;
+      if (cfg.U2 >= 0) *reinterpret_cast<double2*>(pp + cfg.U2 * PP_BYTES + off) = u2;
+      if (cfg.CL >= 0) *reinterpret_cast<double2*>(pp + cfg.CL * PP_BYTES + off) = cl;
+      if (cfg.RDP >= 0) *reinterpret_cast<double2*>(pp + cfg.RDP * PP_BYTES + off) = rd;
     }
   }
 
-  // ---- per-thread DSS gather offsets (bytes inside a stage buffer) ------------------------------------------------
-  int goff[NSLOT];
+  // ---- per-thread DSS gather offsets (bytes inside the IN buffer), two 16-bit offsets per register ----------------
+  unsigned goff[NSLOT / 2];
   {
     const int* gs = tb.gsrc_t + (size_t)(evalid ? e : 0) * NSLOT;
     TSE_UNROLL
@@ -269,33 +350,75 @@ __global__ void __launch_bounds__(TT, 2) k_tile(Geo G, Dvv D, TileTables tb, Til
         const int p2 = qi * GPL + (code >> 4) * KC + kk, node = code & 15;
         off = p2 * 128 + ((((node >> 1) ^ (p2 & 7))) << 4) + (node & 1) * 8;
       }
-      goff[s] = off;
+      // IN buffer is < 512 KB / 8: store offsets in units of 8 bytes
+      if (s & 1) goff[s >> 1] |= (unsigned)(off >> 3) << 16;
+      else goff[s >> 1] = (unsigned)(off >> 3);
     }
   }
-  const unsigned smem_u32 = (unsigned)__cvta_generic_to_shared(smem);
+  auto gofs = [&](int s) -> int { return (int)(((s & 1) ? (goff[s >> 1] >> 16) : (goff[s >> 1] & 0xffffu)) << 3); };
 
+  // ---- halo entries handled by this thread: entry idx -> (h = idx % H, kk2 = idx / H), h fastest for coalescing --------
+  const int nhalo = H * KC;
+  long long hsrc[HPRE];  // double index of the source for tracer 0 (>= 0: in field; < 0: -(index in ghost array) - 1)
+  int hdst[HPRE];        // byte offset in the IN buffer for tracer slot 0
+  TSE_UNROLL
+  for (int r = 0; r < HPRE; ++r) {
+    const int idx = t + r * TT;
+    hsrc[r] = 0;
+    hdst[r] = -1;
+    if (idx < nhalo) {
+      const int h = idx % H, kk2 = idx / H;
+      const int code = tb.halo_src[hoff + h];
+      const int kq = kc * KC + kk2;
+      hdst[r] = TILE_BYTES + (h * KC + kk2) * 8;
+      if (code >= 0) hsrc[r] = (long long)(qplane(code >> 4, 0, kq, Q) * 16 + (code & 15));
+      else hsrc[r] = -((long long)(-code - 2) * Q * NLEV + kq) - 1;
+    }
+  }
+
+  const unsigned smem_u32 = (unsigned)__cvta_generic_to_shared(smem);
   const int nit = (Q + QI - 1) / QI;
   const int nitems = nit * NIN;
+  const size_t cta_base = ((size_t)g * NKC + kc) * Q * GPL * 16;  // doubles
+  // own-plane chunk offsets
+  const int own_base = p * 128, own_sw = p & 7;
+  const int cp_dst0 = (t >> 3) * 128 + (((t & 7) ^ ((t >> 3) & 7)) << 4);
+  const bool group_full = (g * GE + GE <= G.nelem);
+
   auto issue = [&](int j) {
     const int it = j / NIN, which = j % NIN;
     const double* src = a.src[which];
     const int q0 = it * QI, nq = min(QI, Q - q0);
-    const unsigned dst = smem_u32 + (j & 1) * SB;
-    const size_t base = (((size_t)g * NKC + kc) * Q + q0) * GPL * 16;
-    TSE_UNROLL
-    for (int r = 0; r < 8; ++r) {
-      const int i = r * TT + t, p = i >> 3, c = i & 7;
-      if (p < nq * GPL) cp_async16(dst + p * 128 + ((c ^ (p & 7)) << 4), src + base + (size_t)i * 2);
+    const double* tsrc = src + cta_base + (size_t)q0 * GPL * 16 + t * 2;
+    // chunk i = r*TT + t -> plane r*TT/8 + (t>>3), 16-byte unit t&7: the swizzle term does not depend on r
+    if (nq == QI) {
+      TSE_UNROLL
+      for (int r = 0; r < 8; ++r) cp_async16(smem_u32 + cp_dst0 + r * (TT * 16), tsrc + r * (TT * 2));
+    } else {
+      TSE_UNROLL
+      for (int r = 0; r < 8; ++r)
+        if (r * (TT / 8) + (t >> 3) < nq * GPL) cp_async16(smem_u32 + cp_dst0 + r * (TT * 16), tsrc + r * (TT * 2));
     }
     if (a.pending[which]) {
-      const int total = nq * KC * H;
-      for (int idx = t; idx < total; idx += TT) {
-        const int h = idx % H, r2 = idx / H, kk2 = r2 % KC, qi2 = r2 / KC;
+      TSE_UNROLL
+      for (int r = 0; r < HPRE; ++r) {
+        if (hdst[r] >= 0) {
+          for (int qi2 = 0; qi2 < nq; ++qi2) {
+            const double* gp = hsrc[r] >= 0 ? src + hsrc[r] + (size_t)(q0 + qi2) * GPL * 16
+                                            : a.ghost[which] + (-(hsrc[r] + 1)) + (size_t)(q0 + qi2) * NLEV;
+            cp_async8(smem_u32 + hdst[r] + qi2 * tb.hmax * KC * 8, gp);
+          }
+        }
+      }
+      for (int idx = t + HPRE * TT; idx < nhalo; idx += TT) {  // groups with more than HPRE*TT/KC halo nodes (irregular patches)
+        const int h = idx % H, kk2 = idx / H;
         const int code = tb.halo_src[hoff + h];
-        const int kq = kc * KC + kk2, qq = q0 + qi2;
-        const double* gp = (code >= 0) ? src + (qplane(code >> 4, qq, kq, Q) * 16 + (code & 15))
-                                       : a.ghost[which] + ((size_t)(-code - 2) * Q + qq) * NLEV + kq;
-        cp_async8(dst + TILE_BYTES + ((qi2 * tb.hmax + h) * KC + kk2) * 8, gp);
+        const int kq = kc * KC + kk2;
+        for (int qi2 = 0; qi2 < nq; ++qi2) {
+          const double* gp = (code >= 0) ? src + (qplane(code >> 4, q0 + qi2, kq, Q) * 16 + (code & 15))
+                                         : a.ghost[which] + ((size_t)(-code - 2) * Q + q0 + qi2) * NLEV + kq;
+          cp_async8(smem_u32 + TILE_BYTES + ((qi2 * tb.hmax + h) * KC + kk2) * 8, gp);
+        }
       }
     }
     cp_async_commit();
@@ -305,82 +428,80 @@ __global__ void __launch_bounds__(TT, 2) k_tile(Geo G, Dvv D, TileTables tb, Til
   double sumc = 0.0;
   __syncthreads();  // package visible
   if (kStage) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     TSE_UNROLL
-    for (int k1 = 0; k1 < 16; ++k1) {
-      const int n = (k1 >> 2) + 4 * (k1 & 3);
-      sumc += lds64(pp + PP_CL * PP_BYTES, ((n >> 1) * GPL + pl) * 16 + (n & 1) * 8);
+    for (int c = 0; c < 8; c += 2) {
+      const double2 x0 = lds128(pp + cfg.CL * PP_BYTES, (c * GPL + pl) * 16);
+      const double2 x1 = lds128(pp + cfg.CL * PP_BYTES, ((c + 1) * GPL + pl) * 16);
+      s0 += x0.x; s1 += x0.y; s2 += x1.x; s3 += x1.y;
     }
+    sumc = (s0 + s1) + (s2 + s3);
   }
   const double cf = (OP == OP_STAGE3) ? a.visc_coef * a.dp0[k] : 0.0;
 
   double keep[16];  // STAGE3: cf*lap of the first item; TIME_AVG: Qdp(n0)
   issue(0);
   for (int j = 0; j < nitems; ++j) {
-    if (j + 1 < nitems) {
-      issue(j + 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
+    cp_async_wait_all();
+    __syncthreads();  // IN holds item j; every thread is past the copy-out of the previous item
     const int it = j / NIN, which = j % NIN;
     const int q = it * QI + qi;
     const bool valid = evalid && q < Q;
-    const unsigned char* buf = smem + (j & 1) * SB;
     const size_t pidx = (((size_t)g * NKC + kc) * Q + q) * GPL + pl;  // global plane index
 
     double S[16];
     TSE_UNROLL
     for (int c = 0; c < 8; ++c) {
-      const double2 v = lds128(buf, t * 128 + ((c ^ (t & 7)) << 4));
+      const double2 v = lds128(smem, own_base + ((c ^ own_sw) << 4));
       S[2 * c] = v.x;
       S[2 * c + 1] = v.y;
     }
     if (a.pending[which]) {  // DSS in the reference's unpack order: S, E, N, W edges, then SW, SE, NE, NW corners
       TSE_UNROLL
-      for (int i = 0; i < 4; ++i) S[i] += lds64(buf, goff[i]);
+      for (int i = 0; i < 4; ++i) S[i] += lds64(smem, gofs(i));
       TSE_UNROLL
-      for (int i = 0; i < 4; ++i) S[3 + 4 * i] += lds64(buf, goff[4 + i]);
+      for (int i = 0; i < 4; ++i) S[3 + 4 * i] += lds64(smem, gofs(4 + i));
       TSE_UNROLL
-      for (int i = 0; i < 4; ++i) S[12 + i] += lds64(buf, goff[8 + i]);
+      for (int i = 0; i < 4; ++i) S[12 + i] += lds64(smem, gofs(8 + i));
       TSE_UNROLL
-      for (int i = 0; i < 4; ++i) S[4 * i] += lds64(buf, goff[12 + i]);
-      S[0] += lds64(buf, goff[16]);
-      S[3] += lds64(buf, goff[17]);
-      S[15] += lds64(buf, goff[18]);
-      S[12] += lds64(buf, goff[19]);
+      for (int i = 0; i < 4; ++i) S[4 * i] += lds64(smem, gofs(12 + i));
+      S[0] += lds64(smem, gofs(16));
+      S[3] += lds64(smem, gofs(17));
+      S[15] += lds64(smem, gofs(18));
+      S[12] += lds64(smem, gofs(19));
     }
-    const bool last_of_iter = (which == NIN - 1);
-    if (kHasOut && last_of_iter) __syncthreads();  // everyone has read this buffer; it becomes the output staging tile
+    __syncthreads();  // all reads of IN done: prefetch the next item into it, overlapping the compute below
+    if (j + 1 < nitems) issue(j + 1);
 
+    const bool last_of_iter = (which == NIN - 1);
     if (valid) {
       if (OP == OP_MINMAX || OP == OP_BIHARM_PRE) {
-        double mn, mx;
         TSE_UNROLL
         for (int c = 0; c < 8; ++c) {
-          const double2 rd = lds128(pp + PP_RDP * PP_BYTES, (c * GPL + pl) * 16);
+          const double2 rd = lds128(pp + cfg.RDP * PP_BYTES, (c * GPL + pl) * 16);
           S[2 * c] *= rd.x;
           S[2 * c + 1] *= rd.y;
         }
-        mn = S[0];
-        mx = S[0];
+        double mn0 = fmin(S[0], S[1]), mx0 = fmax(S[0], S[1]), mn1 = fmin(S[2], S[3]), mx1 = fmax(S[2], S[3]);
         TSE_UNROLL
-        for (int n = 1; n < 16; ++n) {
-          mn = fmin(mn, S[n]);
-          mx = fmax(mx, S[n]);
+        for (int n = 4; n < 16; n += 4) {
+          mn0 = fmin(mn0, fmin(S[n], S[n + 1]));
+          mx0 = fmax(mx0, fmax(S[n], S[n + 1]));
+          mn1 = fmin(mn1, fmin(S[n + 2], S[n + 3]));
+          mx1 = fmax(mx1, fmax(S[n + 2], S[n + 3]));
         }
-        a.qmin_loc[pidx] = mn;
-        a.qmax_loc[pidx] = mx;
+        a.qmin_loc[pidx] = fmin(mn0, mn1);
+        a.qmax_loc[pidx] = fmax(mx0, mx1);
         if (OP == OP_BIHARM_PRE) {
           double lap[16];
-          laplace_wk_el(S, D, elb, el, lap);
+          laplace_wk_el(S, D, elb + cfg.T11 * EL_BYTES, elb + cfg.T12 * EL_BYTES, elb + cfg.T22 * EL_BYTES, el, lap);
           TSE_UNROLL
           for (int n = 0; n < 16; ++n) S[n] = lap[n];
         }
       } else if (OP == OP_RESOLVE) {
         TSE_UNROLL
         for (int c = 0; c < 8; ++c) {
-          const double2 rs = lds128(elb + EL_RSPH * EL_BYTES, (c * GE + el) * 16);
+          const double2 rs = lds128(elb + cfg.RSPH * EL_BYTES, (c * GE + el) * 16);
           S[2 * c] *= rs.x;
           S[2 * c + 1] *= rs.y;
         }
@@ -391,7 +512,7 @@ __global__ void __launch_bounds__(TT, 2) k_tile(Geo G, Dvv D, TileTables tb, Til
         } else {
           TSE_UNROLL
           for (int c = 0; c < 8; ++c) {
-            double2 rs = lds128(elb + EL_RSPH * EL_BYTES, (c * GE + el) * 16);
+            double2 rs = lds128(elb + cfg.RSPH * EL_BYTES, (c * GE + el) * 16);
             if (!a.pending[1]) rs = make_double2(1.0, 1.0);
             S[2 * c] = (keep[2 * c] + (a.rkstage - 1.0) * (rs.x * S[2 * c])) / a.rkstage;
             S[2 * c + 1] = (keep[2 * c + 1] + (a.rkstage - 1.0) * (rs.y * S[2 * c + 1])) / a.rkstage;
@@ -401,54 +522,45 @@ __global__ void __launch_bounds__(TT, 2) k_tile(Geo G, Dvv D, TileTables tb, Til
         // second half of biharmonic_wk_scalar_minmax: lap(rspheremp*DSS(qtens)); Qtens_biharmonic*spheremp = cf*lap
         TSE_UNROLL
         for (int c = 0; c < 8; ++c) {
-          const double2 rs = lds128(elb + EL_RSPH * EL_BYTES, (c * GE + el) * 16);
+          const double2 rs = lds128(elb + cfg.RSPH * EL_BYTES, (c * GE + el) * 16);
           S[2 * c] *= rs.x;
           S[2 * c + 1] *= rs.y;
         }
         double lap[16];
-        laplace_wk_el(S, D, elb, el, lap);
+        laplace_wk_el(S, D, elb + cfg.T11 * EL_BYTES, elb + cfg.T12 * EL_BYTES, elb + cfg.T22 * EL_BYTES, el, lap);
         TSE_UNROLL
         for (int n = 0; n < 16; ++n) keep[n] = cf * lap[n];
       } else if (kStage) {
         double minp = a.qmin[pidx], maxp = a.qmax[pidx];
         if (OP == OP_STAGE2) {
-          double mn, mx;
-          {
-            const double2 rd = lds128(pp + PP_RDP * PP_BYTES, pl * 16);
-            mn = S[0] * rd.x;
-            mx = mn;
-            const double q1 = S[1] * rd.y;
-            mn = fmin(mn, q1);
-            mx = fmax(mx, q1);
-          }
-          TSE_UNROLL
-          for (int c = 1; c < 8; ++c) {
-            const double2 rd = lds128(pp + PP_RDP * PP_BYTES, (c * GPL + pl) * 16);
-            const double q0v = S[2 * c] * rd.x, q1v = S[2 * c + 1] * rd.y;
-            mn = fmin(mn, fmin(q0v, q1v));
-            mx = fmax(mx, fmax(q0v, q1v));
-          }
-          minp = fmin(minp, mn);
-          maxp = fmax(maxp, mx);
-        }
-        double y[16];
-        {
-          double g1[16], g2[16];
+          double mn0 = 1e300, mx0 = -1e300, mn1 = 1e300, mx1 = -1e300;
           TSE_UNROLL
           for (int c = 0; c < 8; ++c) {
-            const double2 u1 = lds128(pp + PP_U1 * PP_BYTES, (c * GPL + pl) * 16);
-            const double2 u2 = lds128(pp + PP_U2 * PP_BYTES, (c * GPL + pl) * 16);
-            g1[2 * c] = u1.x * S[2 * c];
-            g1[2 * c + 1] = u1.y * S[2 * c + 1];
-            g2[2 * c] = u2.x * S[2 * c];
-            g2[2 * c + 1] = u2.y * S[2 * c + 1];
+            const double2 rd = lds128(pp + cfg.RDP * PP_BYTES, (c * GPL + pl) * 16);
+            const double q0v = S[2 * c] * rd.x, q1v = S[2 * c + 1] * rd.y;
+            mn0 = fmin(mn0, q0v);
+            mx0 = fmax(mx0, q0v);
+            mn1 = fmin(mn1, q1v);
+            mx1 = fmax(mx1, q1v);
           }
-          div_contract(g1, g2, D, y);
+          minp = fmin(minp, fmin(mn0, mn1));
+          maxp = fmax(maxp, fmax(mx0, mx1));
         }
+        double y[16];
+        asm volatile("" ::: "memory");
+#ifdef TSE_SKIP_DIV
+        TSE_UNROLL
+        for (int n = 0; n < 16; ++n) y[n] = S[n];
+#else
+        flux_div(S, pp + cfg.U1 * PP_BYTES, pp + cfg.U2 * PP_BYTES, pl, D, y);
+#endif
+        asm volatile("" ::: "memory");
+        const unsigned e1a = smem_u32 + (unsigned)(elb - smem) + cfg.E1 * EL_BYTES + el * 16;
+        const unsigned e2a = smem_u32 + (unsigned)(elb - smem) + cfg.E2 * EL_BYTES + el * 16;
         TSE_UNROLL
         for (int c = 0; c < 8; ++c) {
-          const double2 e1 = lds128(elb + EL_E1 * EL_BYTES, (c * GE + el) * 16);
-          const double2 e2 = lds128(elb + EL_E2 * EL_BYTES, (c * GE + el) * 16);
+          const double2 e1 = lds128v(e1a + c * GE * 16);
+          const double2 e2 = lds128v(e2a + c * GE * 16);
           y[2 * c] = fma(-e2.x, y[2 * c], e1.x * S[2 * c]);
           y[2 * c + 1] = fma(-e2.y, y[2 * c + 1], e1.y * S[2 * c + 1]);
           if (OP == OP_STAGE3) {
@@ -456,11 +568,11 @@ __global__ void __launch_bounds__(TT, 2) k_tile(Geo G, Dvv D, TileTables tb, Til
             y[2 * c + 1] += keep[2 * c + 1];
           }
         }
-        {
-          double c[16];
-          ld_pp(pp + PP_CL * PP_BYTES, pl, c);
-          limiter_y(y, c, sumc, minp, maxp);
-        }
+        asm volatile("" ::: "memory");
+#ifndef TSE_SKIP_LIMITER
+        limiter_y(y, smem_u32 + (unsigned)(pp - smem) + cfg.CL * PP_BYTES + pl * 16, sumc, minp, maxp);
+#endif
+        asm volatile("" ::: "memory");
         a.qmin[pidx] = minp;
         a.qmax[pidx] = maxp;
         TSE_UNROLL
@@ -470,21 +582,24 @@ __global__ void __launch_bounds__(TT, 2) k_tile(Geo G, Dvv D, TileTables tb, Til
 
     if (kHasOut && last_of_iter) {
       if (valid) {
-        unsigned char* wb = smem + (j & 1) * SB;
         TSE_UNROLL
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<double2*>(wb + t * 128 + ((c ^ (t & 7)) << 4)) = make_double2(S[2 * c], S[2 * c + 1]);
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<double2*>(outb + own_base + ((c ^ own_sw) << 4)) = make_double2(S[2 * c], S[2 * c + 1]);
       }
       __syncthreads();
       const int q0 = it * QI, nq = min(QI, Q - q0);
-      const size_t base = (((size_t)g * NKC + kc) * Q + q0) * GPL * 16;
-      TSE_UNROLL
-      for (int r = 0; r < 8; ++r) {
-        const int i = r * TT + t, p = i >> 3, c = i & 7;
-        if (p < nq * GPL && g * GE + ((p / KC) % GE) < G.nelem)
-          *reinterpret_cast<double2*>(a.out + base + (size_t)i * 2) = lds128(buf, p * 128 + ((c ^ (p & 7)) << 4));
+      double* tdst = a.out + cta_base + (size_t)q0 * GPL * 16 + t * 2;
+      if (nq == QI && group_full) {
+        TSE_UNROLL
+        for (int r = 0; r < 8; ++r) *reinterpret_cast<double2*>(tdst + r * (TT * 2)) = lds128(outb, cp_dst0 + r * (TT * 16));
+      } else {
+        TSE_UNROLL
+        for (int r = 0; r < 8; ++r) {
+          const int pi = r * (TT / 8) + (t >> 3);
+          if (pi < nq * GPL && g * GE + ((pi / KC) % GE) < G.nelem)
+            *reinterpret_cast<double2*>(tdst + r * (TT * 2)) = lds128(outb, cp_dst0 + r * (TT * 16));
+        }
       }
     }
-    __syncthreads();  // buffer (j&1) is free for the load issued at the top of the next iteration
   }
 }
 
