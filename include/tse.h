@@ -103,7 +103,9 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
 int tse_finalize(tse_handle h);
 int tse_synchronize(tse_handle h);
 
-/* multi-GPU: one rank per GPU.  id128 is an ncclUniqueId created on rank 0 (tse_comm_unique_id) and broadcast by the host. */
+/* multi-GPU: one rank per GPU, elements split by the host along the space-filling curve (the connectivity of tse_init carries
+ * the exchange cycles).  id128 is an ncclUniqueId created on rank 0 (tse_comm_unique_id) and broadcast by the host (MPI_Bcast in
+ * a Fortran host, torch.distributed in the Python harness).  Must be called before the first compute entry when ncycles > 0. */
 int tse_comm_unique_id(void* id128);
 int tse_comm_init(tse_handle h, int nranks, int rank, const void* id128);
 
@@ -149,6 +151,8 @@ double tse_mark_elapsed_ms(tse_handle h, int a, int b);
 /* derived%vn0 / derived%dp as currently held on the device (e.g. after the device-side prim_advance_exp) */
 int tse_get_wind(tse_handle h, double* vn0, long long s_vn0, double* dp, long long s_dp);
 long long tse_stage_launch_count(tse_handle h);
+/* bytes this rank has sent through the halo exchange so far */
+long long tse_halo_bytes(tse_handle h);
 /* number of kernel launches issued by this handle so far */
 long long tse_launch_count(tse_handle h);
 /* device bytes allocated by this handle */

@@ -47,7 +47,7 @@ EXPORTS = ["tse_last_error", "tse_device_count", "tse_init", "tse_finalize", "ts
            "tse_copy_qdp_h2d", "tse_copy_qdp_d2h", "tse_set_derived", "tse_get_derived", "tse_get_dp3d_ps", "tse_get_qminmax",
            "tse_precompute_divdp", "tse_euler_step", "tse_qdp_time_avg", "tse_vertical_remap", "tse_advec_tracers_remap_rk2",
            "tse_dcmip_init", "tse_prim_run_subcycle", "tse_diag_mass", "tse_diag_qminmax", "tse_timer_ms", "tse_launch_count",
-           "tse_device_bytes", "tse_timer_reset", "tse_mark", "tse_mark_elapsed_ms", "tse_get_wind", "tse_stage_launch_count"]
+           "tse_device_bytes", "tse_timer_reset", "tse_mark", "tse_mark_elapsed_ms", "tse_get_wind", "tse_stage_launch_count", "tse_halo_bytes"]
 
 
 def cuda_lib():
@@ -94,6 +94,8 @@ def cuda_lib():
         L.tse_mark_elapsed_ms.argtypes = [vp, i, i]
         L.tse_mark_elapsed_ms.restype = d
         L.tse_get_wind.argtypes = [vp, _dp, ll, _dp, ll]
+        L.tse_halo_bytes.argtypes = [vp]
+        L.tse_halo_bytes.restype = ll
         _LIB = L
     return _LIB
 
@@ -149,6 +151,20 @@ class TracerAdvection:
             self.close()
         except Exception:
             pass
+
+    def comm_init(self, dist, rank, world):
+        """Multi-GPU: broadcast rank 0's ncclUniqueId over torch.distributed (plumbing only) and create the halo communicator."""
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            self._ck(self._L.tse_comm_unique_id(buf))
+        box = [bytes(buf)]
+        dist.broadcast_object_list(box, src=0)
+        idb = (C.c_ubyte * 128).from_buffer_copy(box[0])
+        self._ck(self._L.tse_comm_init(self._h, world, rank, idb))
+
+    @property
+    def halo_bytes(self):
+        return self._L.tse_halo_bytes(self._h)
 
     # --- cuda_mod hooks -------------------------------------------------------------------
     def copy_qdp_h2d(self, Qdp, tl):

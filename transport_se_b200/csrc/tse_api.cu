@@ -1,10 +1,23 @@
 // C ABI of the B200 tracer-advection path (see include/tse.h for the reference hooks each entry replaces).
+//
+// State lives in HBM for the whole run (tse_state).  Tracer fields use a pool of 4 buffers: the two Qdp time levels, the
+// stage output (a stage cannot run in place because neighbours gather from its input) and the biharmonic temporary.
+// A time-level slot may be "pending": its buffer holds the pre-DSS output of an RK stage and the DSS is applied by
+// whichever kernel reads it next (or by an explicit resolve when the host asks for the field).
+//
+// Multi-GPU: one rank per GPU, elements split along the space-filling curve by the host.  The only data-path
+// communication is the halo of each DSS (5 per tracer step, like the reference's 5 bndry_exchangeV calls): the boundary
+// nodes facing another rank are packed into a send slab per neighbour rank and moved with ncclSend/ncclRecv into the ghost
+// array the consumer kernels gather from.  Ghost values are bit copies and sums keep the reference's unpack order, so
+// results are bit-for-bit identical for any number of GPUs.
 #include <cuda_runtime.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -34,10 +47,15 @@ int fail(const char* fmt, ...) {
   return 1;
 }
 
-#define CU(call)                                                                                       \
-  do {                                                                                                 \
-    cudaError_t _e = (call);                                                                           \
+#define CU(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t _e = (call);                                                                              \
     if (_e != cudaSuccess) return fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+  } while (0)
+#define NC(call)                                                                                          \
+  do {                                                                                                    \
+    ncclResult_t _e = (call);                                                                             \
+    if (_e != ncclSuccess) return fail("%s:%d %s: %s", __FILE__, __LINE__, #call, ncclGetErrorString(_e)); \
   } while (0)
 
 const double kRearth = 6.376e6;  // physical_constants.F90:16-34
@@ -51,44 +69,48 @@ struct tse_state {
   cudaStream_t stream = nullptr;
   Geo geo{};
   Dvv dvv{};
+  TileTables tiles{};
   std::vector<int> h2i;  // host element -> internal element
   int* d_h2i = nullptr;
-  // tracer buffers: 2 time levels + stage ping-pong + biharmonic temporary
+  // tracer buffers
   double* qbuf[4] = {nullptr, nullptr, nullptr, nullptr};
+  double* qghost[4] = {nullptr, nullptr, nullptr, nullptr};  // halo of each buffer when it is pending (multi-GPU)
   size_t qdoubles = 0;
-  int slot_buf[3] = {-1, 0, 1};      // [tl] (1-based) -> buffer
-  int slot_pending[3] = {0, 0, 0};   // [tl] buffer holds pre-DSS values
+  int slot_buf[3] = {-1, 0, 1};     // [tl] (1-based) -> buffer
+  int slot_pending[3] = {0, 0, 0};  // [tl] buffer holds pre-DSS values
   // level fields
   size_t ldoubles = 0;
-  double *vn0 = nullptr, *dp = nullptr, *divdp = nullptr, *divdp_proj = nullptr, *eta_dot = nullptr, *omega_p = nullptr,
-         *lev_tmp = nullptr, *dp3d = nullptr, *ps_v = nullptr, *pkg = nullptr;
+  double *vn0 = nullptr, *dp = nullptr, *divdp = nullptr, *divdp_proj = nullptr, *eta_dot = nullptr, *omega_p = nullptr, *lev_tmp = nullptr,
+         *dp3d = nullptr, *ps_v = nullptr;
   double *qmin = nullptr, *qmax = nullptr, *qmin_loc = nullptr, *qmax_loc = nullptr;
   double *d_dp0 = nullptr, *d_dA = nullptr, *d_dB = nullptr;
-  double hyai0_ps0 = 0;
+  double hyai0_ps0 = 0, ps0 = 0;
   double* stage = nullptr;
   size_t stage_doubles = 0;
   int* d_err = nullptr;
-  long long launches = 0, stage_launches = 0;
-  long long dev_bytes = 0;
-  cudaEvent_t marks[16] = {};
+  long long launches = 0, stage_launches = 0, dev_bytes = 0;
   std::vector<void*> allocs;
+  // halo exchange (multi-GPU)
+  int nranks = 1, rank = 0;
+  ncclComm_t comm = nullptr;
+  struct Cycle { int peer, off, len, boff, blen; };  // ghost-slot range and bundle range exchanged with one neighbour rank
+  std::vector<Cycle> cycles;
+  int nghost = 0, nbundle = 0;
+  int *d_send_src = nullptr, *d_mm_elem = nullptr;
+  double *send_q = nullptr, *send_lev = nullptr, *ghost_lev = nullptr, *send_mm = nullptr, *ghost_mm = nullptr;
+  long long halo_bytes = 0;  // bytes sent by this rank so far
+  // timers (lazily resolved CUDA events under the reference's GPTL names)
   std::map<std::string, double> timers;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  // lazily resolved CUDA-event timers under the reference's GPTL names
   struct TimerRec { const char* name; cudaEvent_t a, b; };
   std::vector<TimerRec> timer_pending;
   std::vector<cudaEvent_t> event_pool;
-  // prescribed-wind test case (tse_dcmip_init)
+  cudaEvent_t marks[16] = {};
+  // prescribed-wind test case
   int test_case = 0;
   double *d_lon = nullptr, *d_lat = nullptr;
   DcmipTables dcmip{};
   std::vector<double> hv_hyai, hv_hybi, hv_hyam, hv_hybm;
-  double ps0 = 0;
   bool have_latlon = false;
-  // tiled kernels
-  TileTables tiles{};
-  int tile_smem = 0;
-  bool use_tiled = true;
   // diagnostics
   unsigned long long* d_maxbits = nullptr;
   long long* d_acc = nullptr;
@@ -100,6 +122,7 @@ namespace {
 template <class T>
 int dalloc(tse_state* s, T** p, size_t count) {
   void* v = nullptr;
+  if (count == 0) count = 1;
   CU(cudaMalloc(&v, count * sizeof(T)));
   CU(cudaMemsetAsync(v, 0, count * sizeof(T), s->stream));
   s->allocs.push_back(v);
@@ -110,7 +133,7 @@ int dalloc(tse_state* s, T** p, size_t count) {
 template <class T>
 int upload(tse_state* s, T** p, const std::vector<T>& h) {
   if (dalloc(s, p, h.size())) return 1;
-  CU(cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+  if (!h.empty()) CU(cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   return 0;
 }
@@ -131,18 +154,13 @@ unsigned level_blocks(const tse_state* s) { return (unsigned)(((size_t)s->ngroup
 DssView view(const tse_state* s, int buf, int pending) {
   DssView v;
   v.q = s->qbuf[buf];
-  v.ghost = nullptr;
+  v.ghost = s->qghost[buf];
   v.pending = pending;
   v.Q = s->Q;
   return v;
 }
-MinMaxIO mmio(const tse_state* s) {
-  MinMaxIO m;
-  m.qmin = s->qmin; m.qmax = s->qmax; m.qmin_loc = s->qmin_loc; m.qmax_loc = s->qmax_loc; m.ghost_mm = nullptr;
-  return m;
-}
 
-int pick_buffer(const tse_state* s, std::initializer_list<int> protect) {
+int pick_buffer(std::initializer_list<int> protect) {
   for (int b = 0; b < 4; ++b) {
     bool ok = true;
     for (int p : protect)
@@ -152,47 +170,9 @@ int pick_buffer(const tse_state* s, std::initializer_list<int> protect) {
   return -1;
 }
 
-TileArgs tile_args(const tse_state* s) {
-  TileArgs a{};
-  a.vn0 = s->vn0; a.dp = s->dp; a.divdp = s->divdp; a.divdp_proj = s->divdp_proj;
-  a.dp0 = s->d_dp0;
-  a.qmin = s->qmin; a.qmax = s->qmax; a.qmin_loc = s->qmin_loc; a.qmax_loc = s->qmax_loc;
-  a.Q = s->Q;
-  a.rkstage = 3.0;
-  return a;
-}
-template <int OP>
-void launch_tile(tse_state* s, const TileArgs& a) {
-  k_tile<OP><<<s->ngroups * NKC, TT, tile_smem_bytes(OP, s->tiles.hmax), s->stream>>>(s->geo, s->dvv, s->tiles, a);
-  ++s->launches;
-}
-void launch_nbr_minmax(tse_state* s) {
-  const size_t total = (size_t)s->ngroups * NKC * s->Q * GPL;
-  k_nbr_minmax<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(s->geo, s->Q, s->qmin_loc, s->qmax_loc, nullptr, s->qmin, s->qmax);
-  ++s->launches;
-}
-
 int check_tl(int tl) { return (tl == 1 || tl == 2) ? 0 : fail("time level %d out of range (1|2)", tl); }
 
-int resolve_slot(tse_state* s, int tl) {
-  if (!s->slot_pending[tl]) return 0;
-  const int other = s->slot_buf[3 - tl];
-  const int in = s->slot_buf[tl];
-  const int out = pick_buffer(s, {in, other});
-  if (s->use_tiled) {
-    TileArgs a = tile_args(s);
-    a.src[0] = s->qbuf[in]; a.pending[0] = 1; a.out = s->qbuf[out];
-    launch_tile<OP_RESOLVE>(s, a);
-  } else {
-    k_resolve<<<plane_grid(s), GPL * QPB, 0, s->stream>>>(s->geo, view(s, in, 1), s->qbuf[out]);
-    ++s->launches;
-  }
-  CU(cudaGetLastError());
-  s->slot_buf[tl] = out;
-  s->slot_pending[tl] = 0;
-  return 0;
-}
-
+// ---- timers -----------------------------------------------------------------------------------
 cudaEvent_t get_event(tse_state* s) {
   if (!s->event_pool.empty()) {
     cudaEvent_t e = s->event_pool.back();
@@ -239,60 +219,99 @@ int check_device_error(tse_state* s) {
   return 0;
 }
 
-
-
-int dss_level_field(tse_state* s, int DSSopt) {
-  // DSS of the extra level field (prim_advection_mod.F90:913-919, 943-958)
-  double** f = DSSopt == TSE_DSS_ETA ? &s->eta_dot : DSSopt == TSE_DSS_OMEGA ? &s->omega_p : DSSopt == TSE_DSS_DIV_VDP_AVE ? &s->divdp_proj : nullptr;
-  if (DSSopt != TSE_DSS_NO_VAR && !f) return fail("tse_euler_step: DSSopt=%d", DSSopt);
-  if (f) {
-    k_dss_level<<<level_blocks(s), 128, 0, s->stream>>>(s->geo, *f, nullptr, s->lev_tmp);
-    ++s->launches;
-    CU(cudaGetLastError());
-    std::swap(*f, s->lev_tmp);
+// ---- halo exchange ----------------------------------------------------------------------------
+// one ncclSend + ncclRecv per neighbour rank (a Cycle_t of the reference's schedule), `unit` doubles per ghost slot / bundle
+int exchange(tse_state* s, const double* send, double* recv, size_t unit, bool bundles) {
+  if (s->cycles.empty()) return 0;
+  if (!s->comm) return fail("halo exchange: this rank has off-GPU neighbours but tse_comm_init was not called");
+  ScopedTimer tm(s, "bndry_exchange");
+  NC(ncclGroupStart());
+  for (const auto& c : s->cycles) {
+    const size_t off = (size_t)(bundles ? c.boff : c.off) * unit, cnt = (size_t)(bundles ? c.blen : c.len) * unit;
+    NC(ncclSend(send + off, cnt, ncclDouble, c.peer, s->comm, s->stream));
+    NC(ncclRecv(recv + off, cnt, ncclDouble, c.peer, s->comm, s->stream));
+    s->halo_bytes += (long long)cnt * 8;
   }
+  NC(ncclGroupEnd());
+  return 0;
+}
+// halo of a pre-DSS tracer buffer -> qghost[buf]
+int exchange_tracer(tse_state* s, int buf) {
+  if (s->cycles.empty()) return 0;
+  const size_t total = (size_t)s->nghost * s->Q * NLEV;
+  k_pack_tracer<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(s->qbuf[buf], s->d_send_src, s->nghost, s->Q, s->send_q);
+  ++s->launches;
+  CU(cudaGetLastError());
+  return exchange(s, s->send_q, s->qghost[buf], (size_t)s->Q * NLEV, false);
+}
+int exchange_minmax(tse_state* s) {
+  if (s->cycles.empty()) return 0;
+  const size_t total = (size_t)s->nbundle * s->Q * NLEV;
+  k_pack_minmax<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(s->qmin_loc, s->qmax_loc, s->d_mm_elem, s->nbundle, s->Q, s->send_mm);
+  ++s->launches;
+  CU(cudaGetLastError());
+  return exchange(s, s->send_mm, s->ghost_mm, (size_t)2 * s->Q * NLEV, true);
+}
+
+TileArgs tile_args(const tse_state* s) {
+  TileArgs a{};
+  a.vn0 = s->vn0; a.dp = s->dp; a.divdp = s->divdp; a.divdp_proj = s->divdp_proj;
+  a.dp0 = s->d_dp0;
+  a.qmin = s->qmin; a.qmax = s->qmax; a.qmin_loc = s->qmin_loc; a.qmax_loc = s->qmax_loc;
+  a.Q = s->Q;
+  a.rkstage = 3.0;
+  return a;
+}
+void set_src(const tse_state* s, TileArgs& a, int i, int buf, int pending) {
+  a.src[i] = s->qbuf[buf];
+  a.ghost[i] = s->qghost[buf];
+  a.pending[i] = pending;
+}
+template <int OP>
+void launch_tile(tse_state* s, const TileArgs& a) {
+  k_tile<OP><<<s->ngroups * NKC, TT, tile_smem_bytes(OP, s->tiles.hmax), s->stream>>>(s->geo, s->dvv, s->tiles, a);
+  ++s->launches;
+}
+// neighbor_minmax (viscosity_mod.F90:748-816): exchange of the element extrema + 9-way min/max
+int neighbor_minmax(tse_state* s) {
+  if (exchange_minmax(s)) return 1;
+  const size_t total = (size_t)s->ngroups * NKC * s->Q * GPL;
+  k_nbr_minmax<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(s->geo, s->Q, s->qmin_loc, s->qmax_loc, s->ghost_mm, s->qmin, s->qmax);
+  ++s->launches;
+  CU(cudaGetLastError());
   return 0;
 }
 
-int euler_step_tiled(tse_state* s, int np1_qdp, int n0_qdp, double dt, int DSSopt, int rhs_multiplier) {
-  const int in = s->slot_buf[n0_qdp], in_pending = s->slot_pending[n0_qdp];
-  const int other = (np1_qdp == n0_qdp) ? s->slot_buf[3 - np1_qdp] : -1;  // the untouched time level
+int resolve_slot(tse_state* s, int tl) {
+  if (!s->slot_pending[tl]) return 0;
+  const int other = s->slot_buf[3 - tl], in = s->slot_buf[tl];
+  const int out = pick_buffer({in, other});
   TileArgs a = tile_args(s);
-  a.rhs_mult_dt = rhs_multiplier * dt;
-  a.dt = dt;
-  a.visc_coef = -3.0 * dt * s->cfg.nu_q;  // rhs_viss = 3 (prim_advection_mod.F90:797,823)
-  int tmp = -1;
-  if (rhs_multiplier == 0) {
-    a.src[0] = s->qbuf[in]; a.pending[0] = in_pending;
-    launch_tile<OP_MINMAX>(s, a);
-    launch_nbr_minmax(s);
-  } else if (rhs_multiplier == 2) {
-    tmp = pick_buffer(s, {in, other});
-    if (tmp < 0) return fail("tse_euler_step: no free tracer buffer");
-    a.src[0] = s->qbuf[in]; a.pending[0] = in_pending; a.out = s->qbuf[tmp];
-    launch_tile<OP_BIHARM_PRE>(s, a);
-    launch_nbr_minmax(s);
-  }
-  const int outb = pick_buffer(s, {in, other, tmp});
-  if (outb < 0) return fail("tse_euler_step: no free tracer buffer");
-  a.out = s->qbuf[outb];
-  {
-    ScopedTimer tk(s, "k_euler_stage");
-    if (rhs_multiplier == 2) {
-      a.src[0] = s->qbuf[tmp]; a.pending[0] = 1;
-      a.src[1] = s->qbuf[in]; a.pending[1] = in_pending;
-      launch_tile<OP_STAGE3>(s, a);
-    } else {
-      a.src[0] = s->qbuf[in]; a.pending[0] = in_pending;
-      if (rhs_multiplier == 0) launch_tile<OP_STAGE1>(s, a);
-      else launch_tile<OP_STAGE2>(s, a);
-    }
-    ++s->stage_launches;
-  }
+  set_src(s, a, 0, in, 1);
+  a.out = s->qbuf[out];
+  launch_tile<OP_RESOLVE>(s, a);
   CU(cudaGetLastError());
-  s->slot_buf[np1_qdp] = outb;
-  s->slot_pending[np1_qdp] = 1;
-  return dss_level_field(s, DSSopt);
+  s->slot_buf[tl] = out;
+  s->slot_pending[tl] = 0;
+  return 0;
+}
+
+// DSS of the extra level field of euler_step (prim_advection_mod.F90:913-919, 943-958)
+int dss_level_field(tse_state* s, int DSSopt) {
+  double** f = DSSopt == TSE_DSS_ETA ? &s->eta_dot : DSSopt == TSE_DSS_OMEGA ? &s->omega_p : DSSopt == TSE_DSS_DIV_VDP_AVE ? &s->divdp_proj : nullptr;
+  if (DSSopt != TSE_DSS_NO_VAR && !f) return fail("tse_euler_step: DSSopt=%d", DSSopt);
+  if (!f) return 0;
+  if (!s->cycles.empty()) {
+    const size_t total = (size_t)s->nghost * NLEV;
+    k_pack_level<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(*f, s->geo.spheremp, s->d_send_src, s->nghost, s->send_lev);
+    ++s->launches;
+    if (exchange(s, s->send_lev, s->ghost_lev, NLEV, false)) return 1;
+  }
+  k_dss_level<<<level_blocks(s), 128, 0, s->stream>>>(s->geo, *f, s->ghost_lev, s->lev_tmp);
+  ++s->launches;
+  CU(cudaGetLastError());
+  std::swap(*f, s->lev_tmp);
+  return 0;
 }
 
 }  // namespace
@@ -327,8 +346,6 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
   s->npad = s->ngroups * GE;
   s->Q = cfg->qsize;
   CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-  CU(cudaEventCreate(&s->ev0));
-  CU(cudaEventCreate(&s->ev1));
   std::memcpy(s->dvv.d, dvv, sizeof s->dvv.d);
   const int ne = s->nelem;
 
@@ -342,14 +359,13 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
 
   // geometry
   const size_t n16 = (size_t)s->npad * 16;
-  std::vector<double> sp(n16, 1.0), rsp(n16, 1.0), rmp(n16, 1.0), rmr(n16, 0.0), mD((size_t)s->npad * 64, 0.0), T((size_t)s->npad * 48, 0.0);
+  std::vector<double> sp(n16, 1.0), rsp(n16, 1.0), rmr(n16, 0.0), mD((size_t)s->npad * 64, 0.0), T((size_t)s->npad * 48, 0.0);
   for (int eh = 0; eh < ne; ++eh) {
     const int e = s->h2i[eh];
     for (int n = 0; n < 16; ++n) {
       const size_t hi = (size_t)eh * 16 + n, di = (size_t)e * 16 + n;
       sp[di] = geom->spheremp[hi];
       rsp[di] = geom->rspheremp[hi];
-      rmp[di] = 1.0 / geom->spheremp[hi];
       rmr[di] = geom->rmetdet[hi] * kRrearth;
       const double* Di = geom->Dinv + hi * 4;  // Dinv(a,b) at [a + 2b]
       const double d11 = Di[0], d21 = Di[1], d12 = Di[2], d22 = Di[3];
@@ -364,22 +380,21 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
       T[(size_t)e * 48 + 32 + n] = f * (d21 * d21 + d22 * d22);
     }
   }
-  double *d_sp, *d_rsp, *d_rmp, *d_rmr, *d_mD, *d_T;
-  if (upload(s, &d_sp, sp) || upload(s, &d_rsp, rsp) || upload(s, &d_rmp, rmp) || upload(s, &d_rmr, rmr) || upload(s, &d_mD, mD) ||
-      upload(s, &d_T, T))
-    return 1;
+  double *d_sp, *d_rsp, *d_rmr, *d_mD, *d_T;
+  if (upload(s, &d_sp, sp) || upload(s, &d_rsp, rsp) || upload(s, &d_rmr, rmr) || upload(s, &d_mD, mD) || upload(s, &d_T, T)) return 1;
 
-  // DSS gather table from the reference's put/get maps (edge_mod.F90:366-511 pack, :648-742 unpack)
+  // ---- DSS gather table from the reference's put/get maps (edge_mod.F90:366-511 pack, :648-742 unpack) ----
+  // A slot of the edge buffer inside a cycle range [ptrP, ptrP+lengthP) belongs to a neighbour rank: what this rank packs
+  // there is sent (send_src), what it unpacks from there is the neighbour's value (ghost).
   const int nbuf = conn->nbuf;
-  std::vector<int> slot_src(nbuf, -1);
-  std::vector<char> remote(nbuf, 0);
-  std::vector<int> ghost_base(nbuf, -1);
+  std::vector<int> slot_src(nbuf, -1), ghost_id(nbuf, -1);
   int nghost = 0;
-  for (int c = 0; c < conn->ncycles; ++c)
-    for (int i = 0; i < conn->cyc_len[c]; ++i) {
-      remote[conn->cyc_ptr[c] + i] = 1;
-      ghost_base[conn->cyc_ptr[c] + i] = nghost++;
-    }
+  for (int c = 0; c < conn->ncycles; ++c) {
+    if (conn->cyc_ptr[c] < 0 || conn->cyc_ptr[c] + conn->cyc_len[c] > nbuf) return fail("tse_init: exchange cycle out of range");
+    for (int i = 0; i < conn->cyc_len[c]; ++i) ghost_id[conn->cyc_ptr[c] + i] = nghost++;
+  }
+  s->nghost = nghost;
+  std::vector<int> send_src(nghost, 0);
   for (int eh = 0; eh < ne; ++eh)
     for (int d = 0; d < 8; ++d) {
       const int pm = conn->putmapP[eh * 8 + d];
@@ -388,10 +403,41 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
       if (pm + len > nbuf) return fail("tse_init: putmapP out of range");
       for (int i = 0; i < len; ++i) {
         const int t = (d < 4) ? (conn->reverse[eh * 8 + d] ? NP - 1 - i : i) : 0;
-        const int node = d < 4 ? edge_node(d, t) : corner_node(d);
-        if (!remote[pm + i]) slot_src[pm + i] = (s->h2i[eh] << 4) | node;
+        const int code = (s->h2i[eh] << 4) | (d < 4 ? edge_node(d, t) : corner_node(d));
+        if (ghost_id[pm + i] >= 0) send_src[ghost_id[pm + i]] = code;
+        else slot_src[pm + i] = code;
       }
     }
+  // bundles = (element, direction) pairs facing another rank, numbered in ghost-slot order (identical on both sides)
+  std::vector<std::pair<int, int>> bundle_key;  // (first ghost id, host element)
+  for (int eh = 0; eh < ne; ++eh)
+    for (int d = 0; d < 8; ++d) {
+      const int gm = conn->getmapP[eh * 8 + d];
+      if (gm >= 0 && gm < nbuf && ghost_id[gm] >= 0) bundle_key.push_back({ghost_id[gm], eh});
+    }
+  std::sort(bundle_key.begin(), bundle_key.end());
+  s->nbundle = (int)bundle_key.size();
+  std::map<int, int> bundle_of;  // first ghost id -> bundle index
+  std::vector<int> mm_elem(s->nbundle, 0);
+  for (int b = 0; b < s->nbundle; ++b) {
+    bundle_of[bundle_key[b].first] = b;
+    mm_elem[b] = s->h2i[bundle_key[b].second];
+  }
+  {
+    int goff = 0;
+    for (int c = 0; c < conn->ncycles; ++c) {
+      tse_state::Cycle cy;
+      cy.peer = conn->cyc_rank[c];
+      cy.off = goff;
+      cy.len = conn->cyc_len[c];
+      goff += cy.len;
+      auto lo = std::lower_bound(bundle_key.begin(), bundle_key.end(), std::make_pair(cy.off, -1));
+      auto hi = std::lower_bound(bundle_key.begin(), bundle_key.end(), std::make_pair(cy.off + cy.len, -1));
+      cy.boff = (int)(lo - bundle_key.begin());
+      cy.blen = (int)(hi - lo);
+      s->cycles.push_back(cy);
+    }
+  }
   std::vector<int> gsrc((size_t)s->npad * NSLOT, -1), nbr8((size_t)s->npad * 8, -1);
   const int unpack_edges[4] = {SOUTH, EAST, NORTH, WEST};
   const int unpack_corners[4] = {SWEST, SEAST, NEAST, NWEST};
@@ -399,25 +445,29 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
     const int e = s->h2i[eh];
     auto src_of = [&](int b) -> int {
       if (b < 0 || b >= nbuf) return -1;
-      if (remote[b]) return -(ghost_base[b] + 2);
+      if (ghost_id[b] >= 0) return -(ghost_id[b] + 2);
       return slot_src[b];
+    };
+    auto nbr_of = [&](int gm) -> int {  // neighbour element for min/max: local element, ghost bundle or none
+      const int b = src_of(gm);
+      if (b >= 0) return b >> 4;
+      if (b == -1) return -1;
+      return -(bundle_of[ghost_id[gm]] + 2);
     };
     for (int x = 0; x < 4; ++x) {
       const int gm = conn->getmapP[eh * 8 + unpack_edges[x]];
       for (int i = 0; i < 4; ++i) gsrc[(size_t)e * NSLOT + 4 * x + i] = gm < 0 ? -1 : src_of(gm + i);
-      const int b = gm < 0 ? -1 : src_of(gm);
-      nbr8[(size_t)e * 8 + x] = b >= 0 ? (b >> 4) : -1;  // ghosts: filled by tse_comm_init
+      nbr8[(size_t)e * 8 + x] = gm < 0 ? -1 : nbr_of(gm);
     }
     for (int x = 0; x < 4; ++x) {
       const int gm = conn->getmapP[eh * 8 + unpack_corners[x]];
-      const int b = gm < 0 ? -1 : src_of(gm);
-      gsrc[(size_t)e * NSLOT + 16 + x] = b;
-      nbr8[(size_t)e * 8 + 4 + x] = b >= 0 ? (b >> 4) : -1;
+      gsrc[(size_t)e * NSLOT + 16 + x] = gm < 0 ? -1 : src_of(gm);
+      nbr8[(size_t)e * 8 + 4 + x] = gm < 0 ? -1 : nbr_of(gm);
     }
   }
-  if (conn->ncycles > 0) return fail("tse_init: multi-rank connectivity needs tse_comm_init (not in this build yet)");
   int *d_gsrc, *d_nbr8;
-  if (upload(s, &d_gsrc, gsrc) || upload(s, &d_nbr8, nbr8)) return 1;
+  if (upload(s, &d_gsrc, gsrc) || upload(s, &d_nbr8, nbr8) || upload(s, &s->d_send_src, send_src) || upload(s, &s->d_mm_elem, mm_elem))
+    return 1;
   {
     // group-local view of the gather table: sources inside the 16-element group are read from the shared-memory tile,
     // everything else (other groups, other GPUs) goes through a per-group halo list
@@ -450,12 +500,11 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
     int *d_a, *d_b, *d_c;
     if (upload(s, &d_a, gsrc_t) || upload(s, &d_b, halo_off) || upload(s, &d_c, halo_src)) return 1;
     s->tiles.gsrc_t = d_a; s->tiles.halo_off = d_b; s->tiles.halo_src = d_c; s->tiles.hmax = hmax;
-    s->tile_smem = tile_smem_bytes(OP_STAGE2, hmax);
-    if (s->tile_smem > 227 * 1024) return fail("tse_init: halo of %d nodes per group does not fit in shared memory", hmax);
-    const char* env = getenv("TSE_KERNELS");
-    s->use_tiled = !(env && std::string(env) == "v1");
+    if (tile_smem_bytes(OP_STAGE2, hmax) > 227 * 1024 || tile_smem_bytes(OP_STAGE3, hmax) > 227 * 1024)
+      return fail("tse_init: halo of %d nodes per group does not fit in shared memory", hmax);
+    if (tile_in_bytes(hmax) / 8 >= 65536) return fail("tse_init: halo of %d nodes per group overflows the gather offsets", hmax);
   }
-  s->geo.spheremp = d_sp; s->geo.rspheremp = d_rsp; s->geo.rmp = d_rmp; s->geo.rmr = d_rmr; s->geo.mD = d_mD; s->geo.T = d_T;
+  s->geo.spheremp = d_sp; s->geo.rspheremp = d_rsp; s->geo.rmr = d_rmr; s->geo.mD = d_mD; s->geo.T = d_T;
   s->geo.gsrc = d_gsrc; s->geo.nbr8 = d_nbr8; s->geo.nelem = ne; s->geo.ngroups = s->ngroups;
 
   // vertical coordinate
@@ -483,38 +532,46 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
     if (upload(s, &s->d_lat, la) || upload(s, &s->d_lon, lo)) return 1;
     s->have_latlon = true;
   }
-  if (dalloc(s, &s->d_maxbits, (size_t)s->Q) || dalloc(s, &s->d_acc, (size_t)2 * s->Q) || dalloc(s, &s->d_shift, (size_t)s->Q)) return 1;
   if (upload(s, &s->d_dp0, dp0) || upload(s, &s->d_dA, dA) || upload(s, &s->d_dB, dB)) return 1;
+  if (dalloc(s, &s->d_maxbits, (size_t)s->Q) || dalloc(s, &s->d_acc, (size_t)2 * s->Q) || dalloc(s, &s->d_shift, (size_t)s->Q)) return 1;
 
   // state
   s->ldoubles = (size_t)s->ngroups * NKC * GPL * 16;
   s->qdoubles = s->ldoubles * s->Q;
+  if (s->qdoubles >= ((size_t)1 << 35)) return fail("tse_init: tracer field too large for one GPU (%zu doubles)", s->qdoubles);
   for (int b = 0; b < 4; ++b)
     if (dalloc(s, &s->qbuf[b], s->qdoubles)) return 1;
   if (dalloc(s, &s->vn0, 2 * s->ldoubles) || dalloc(s, &s->dp, s->ldoubles) || dalloc(s, &s->divdp, s->ldoubles) ||
       dalloc(s, &s->divdp_proj, s->ldoubles) || dalloc(s, &s->eta_dot, s->ldoubles) || dalloc(s, &s->omega_p, s->ldoubles) ||
-      dalloc(s, &s->lev_tmp, s->ldoubles) || dalloc(s, &s->dp3d, s->ldoubles) || dalloc(s, &s->ps_v, (size_t)s->npad * 16) ||
-      dalloc(s, &s->pkg, NPKG * s->ldoubles))
+      dalloc(s, &s->lev_tmp, s->ldoubles) || dalloc(s, &s->dp3d, s->ldoubles) || dalloc(s, &s->ps_v, (size_t)s->npad * 16))
     return 1;
   const size_t nplanes = s->qdoubles / 16;
   if (dalloc(s, &s->qmin, nplanes) || dalloc(s, &s->qmax, nplanes) || dalloc(s, &s->qmin_loc, nplanes) || dalloc(s, &s->qmax_loc, nplanes))
     return 1;
   if (dalloc(s, &s->d_err, 1)) return 1;
-  // staging buffer for host<->device layout conversion: whole elements, at most ~256 MB
-  {
+  if (nghost > 0) {
+    const size_t gq = (size_t)nghost * s->Q * NLEV;
+    for (int b = 0; b < 4; ++b)
+      if (dalloc(s, &s->qghost[b], gq)) return 1;
+    if (dalloc(s, &s->send_q, gq) || dalloc(s, &s->send_lev, (size_t)nghost * NLEV) || dalloc(s, &s->ghost_lev, (size_t)nghost * NLEV) ||
+        dalloc(s, &s->send_mm, (size_t)s->nbundle * 2 * s->Q * NLEV) || dalloc(s, &s->ghost_mm, (size_t)s->nbundle * 2 * s->Q * NLEV))
+      return 1;
+  }
+  {  // staging buffer for host<->device layout conversion: whole elements, ~256 MB at most
     const size_t per_elem = (size_t)16 * NLEV * std::max(s->Q, 2) + 16;
-    size_t ne_chunk = std::max<size_t>(1, std::min<size_t>(ne, ((size_t)32 << 20) / per_elem));
+    const size_t ne_chunk = std::max<size_t>(1, std::min<size_t>(ne, ((size_t)32 << 20) / per_elem));
     s->stage_doubles = ne_chunk * per_elem;
     if (dalloc(s, &s->stage, s->stage_doubles)) return 1;
   }
   CU(cudaFuncSetAttribute(k_vertical_remap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RM_SMEM));
-  CU(cudaFuncSetAttribute(k_tile<OP_MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_MINMAX, s->tiles.hmax)));
-  CU(cudaFuncSetAttribute(k_tile<OP_STAGE1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_STAGE1, s->tiles.hmax)));
-  CU(cudaFuncSetAttribute(k_tile<OP_STAGE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_STAGE2, s->tiles.hmax)));
-  CU(cudaFuncSetAttribute(k_tile<OP_STAGE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_STAGE3, s->tiles.hmax)));
-  CU(cudaFuncSetAttribute(k_tile<OP_BIHARM_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_BIHARM_PRE, s->tiles.hmax)));
-  CU(cudaFuncSetAttribute(k_tile<OP_TIME_AVG>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_TIME_AVG, s->tiles.hmax)));
-  CU(cudaFuncSetAttribute(k_tile<OP_RESOLVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_RESOLVE, s->tiles.hmax)));
+  const int hm = s->tiles.hmax;
+  CU(cudaFuncSetAttribute(k_tile<OP_MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_MINMAX, hm)));
+  CU(cudaFuncSetAttribute(k_tile<OP_STAGE1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_STAGE1, hm)));
+  CU(cudaFuncSetAttribute(k_tile<OP_STAGE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_STAGE2, hm)));
+  CU(cudaFuncSetAttribute(k_tile<OP_STAGE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_STAGE3, hm)));
+  CU(cudaFuncSetAttribute(k_tile<OP_BIHARM_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_BIHARM_PRE, hm)));
+  CU(cudaFuncSetAttribute(k_tile<OP_TIME_AVG>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_TIME_AVG, hm)));
+  CU(cudaFuncSetAttribute(k_tile<OP_RESOLVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_RESOLVE, hm)));
   CU(cudaStreamSynchronize(s->stream));
   *out = s;
   return 0;
@@ -524,10 +581,11 @@ int tse_finalize(tse_handle s) {
   if (!s) return 0;
   cudaStreamSynchronize(s->stream);
   resolve_timers(s);
+  if (s->comm) ncclCommDestroy(s->comm);
   for (cudaEvent_t e : s->event_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->marks)
+    if (e) cudaEventDestroy(e);
   for (void* p : s->allocs) cudaFree(p);
-  cudaEventDestroy(s->ev0);
-  cudaEventDestroy(s->ev1);
   cudaStreamDestroy(s->stream);
   delete s;
   return 0;
@@ -538,8 +596,23 @@ int tse_synchronize(tse_handle s) {
   return check_device_error(s);
 }
 
-int tse_comm_unique_id(void*) { return fail("tse_comm_unique_id: multi-GPU exchange not in this build yet"); }
-int tse_comm_init(tse_handle, int, int, const void*) { return fail("tse_comm_init: multi-GPU exchange not in this build yet"); }
+int tse_comm_unique_id(void* id128) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  NC(ncclGetUniqueId(reinterpret_cast<ncclUniqueId*>(id128)));
+  return 0;
+}
+
+int tse_comm_init(tse_handle s, int nranks, int rank, const void* id128) {
+  if (s->comm) return fail("tse_comm_init: already initialised");
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof id);
+  NC(ncclCommInitRank(&s->comm, nranks, id, rank));
+  s->nranks = nranks;
+  s->rank = rank;
+  for (const auto& c : s->cycles)
+    if (c.peer < 0 || c.peer >= nranks || c.peer == rank) return fail("tse_comm_init: exchange cycle with rank %d", c.peer);
+  return 0;
+}
 
 // ---- host <-> device copies -------------------------------------------------------------------
 static int qdp_copy(tse_state* s, double* host, long long elem_stride, int tl, int to_device) {
@@ -587,7 +660,7 @@ static int level_copy(tse_state* s, double* dev, double* host, long long stride,
       k_level_relayout<<<blocks, 256, 0, s->stream>>>(dev, s->stage, s->d_h2i + e0, (int)n, ncomp, host_nlev, 1);
       ++s->launches;
     } else {
-      // keep host levels beyond NLEV (eta_dot_dpdn(nlev+1)) untouched: copy only the first NLEV*ncomp planes
+      // host levels beyond NLEV (eta_dot_dpdn(nlev+1)) stay untouched: only the first NLEV*ncomp planes are copied back
       k_level_relayout<<<blocks, 256, 0, s->stream>>>(dev, s->stage, s->d_h2i + e0, (int)n, ncomp, host_nlev, 0);
       ++s->launches;
       CU(cudaMemcpy2DAsync(h, (size_t)stride * 8, s->stage, per_elem * 8, (size_t)16 * ncomp * NLEV * 8, n, cudaMemcpyDeviceToHost, s->stream));
@@ -614,6 +687,11 @@ int tse_get_derived(tse_handle s, double* divdp, long long s_divdp, double* proj
   if (level_copy(s, s->eta_dot, eta, s_eta, 1, NLEV + 1, 0)) return 1;
   if (level_copy(s, s->omega_p, omega, s_omega, 1, NLEV, 0)) return 1;
   return 0;
+}
+
+int tse_get_wind(tse_handle s, double* vn0, long long s_vn0, double* dp, long long s_dp) {
+  if (level_copy(s, s->vn0, vn0, s_vn0, 2, NLEV, 0)) return 1;
+  return level_copy(s, s->dp, dp, s_dp, 1, NLEV, 0);
 }
 
 int tse_get_dp3d_ps(tse_handle s, double* dp3d, long long s_dp3d, double* ps_v, long long s_ps) {
@@ -651,79 +729,65 @@ int tse_precompute_divdp(tse_handle s) {
 
 int tse_euler_step(tse_handle s, int np1_qdp, int n0_qdp, double dt, int DSSopt, int rhs_multiplier) {
   if (check_tl(np1_qdp) || check_tl(n0_qdp)) return 1;
-  ScopedTimer tm(s, "euler_step");
   if (rhs_multiplier < 0 || rhs_multiplier > 2) return fail("tse_euler_step: rhs_multiplier=%d", rhs_multiplier);
-  if (s->use_tiled) return euler_step_tiled(s, np1_qdp, n0_qdp, dt, DSSopt, rhs_multiplier);
+  ScopedTimer tm(s, "euler_step");
   const int in = s->slot_buf[n0_qdp], in_pending = s->slot_pending[n0_qdp];
-  const dim3 grid = plane_grid(s);
-  const int threads = GPL * QPB;
-  k_stage_prep<<<level_blocks(s), 128, 0, s->stream>>>(s->geo, s->vn0, s->dp, s->divdp, s->divdp_proj, rhs_multiplier * dt, dt, s->pkg,
-                                                       s->ldoubles);
-  ++s->launches;
-  StageArgs a;
-  a.in = view(s, in, in_pending);
-  a.qtens = view(s, in, 0);
-  a.pkg = s->pkg;
-  a.pkg_stride = s->ldoubles;
-  a.mm = mmio(s);
+  const int other = (np1_qdp == n0_qdp) ? s->slot_buf[3 - np1_qdp] : -1;  // the untouched time level
+  TileArgs a = tile_args(s);
+  a.rhs_mult_dt = rhs_multiplier * dt;
   a.dt = dt;
   a.visc_coef = -3.0 * dt * s->cfg.nu_q;  // rhs_viss = 3 (prim_advection_mod.F90:797,823)
-  a.dp0 = s->d_dp0;
-  const int other = (np1_qdp == n0_qdp) ? s->slot_buf[3 - np1_qdp] : -1;  // the untouched time level
   int tmp = -1;
   if (rhs_multiplier == 0) {
-    k_minmax_local<<<grid, threads, 0, s->stream>>>(s->geo, a.in, s->pkg, s->ldoubles, a.mm);
-    ++s->launches;
+    // qmin/qmax = element extrema of Q = Qdp/dp, then min/max over the 8 neighbours (:764-778)
+    set_src(s, a, 0, in, in_pending);
+    launch_tile<OP_MINMAX>(s, a);
+    if (neighbor_minmax(s)) return 1;
   } else if (rhs_multiplier == 2) {
-    tmp = pick_buffer(s, {in, other, np1_qdp == n0_qdp ? -1 : s->slot_buf[n0_qdp]});
+    // biharmonic_wk_scalar_minmax (viscosity_mod.F90:353-442): lap(Q), one exchange carrying lap + extrema, second lap in the stage kernel
+    tmp = pick_buffer({in, other});
     if (tmp < 0) return fail("tse_euler_step: no free tracer buffer");
-    k_biharm_pre<<<grid, threads, 0, s->stream>>>(s->geo, s->dvv, a.in, s->pkg, s->ldoubles, a.mm, s->qbuf[tmp]);
-    ++s->launches;
-    a.qtens = view(s, tmp, 1);
+    set_src(s, a, 0, in, in_pending);
+    a.out = s->qbuf[tmp];
+    launch_tile<OP_BIHARM_PRE>(s, a);
+    CU(cudaGetLastError());
+    if (exchange_tracer(s, tmp)) return 1;
+    if (neighbor_minmax(s)) return 1;
   }
-  const int outb = pick_buffer(s, {in, other, tmp});
+  const int outb = pick_buffer({in, other, tmp});
   if (outb < 0) return fail("tse_euler_step: no free tracer buffer");
   a.out = s->qbuf[outb];
   {
     ScopedTimer tk(s, "k_euler_stage");
-    if (rhs_multiplier == 0) k_euler_stage<1><<<grid, threads, 0, s->stream>>>(s->geo, s->dvv, a);
-    else if (rhs_multiplier == 1) k_euler_stage<2><<<grid, threads, 0, s->stream>>>(s->geo, s->dvv, a);
-    else k_euler_stage<3><<<grid, threads, 0, s->stream>>>(s->geo, s->dvv, a);
-    ++s->launches;
+    if (rhs_multiplier == 2) {
+      set_src(s, a, 0, tmp, 1);
+      set_src(s, a, 1, in, in_pending);
+      launch_tile<OP_STAGE3>(s, a);
+    } else {
+      set_src(s, a, 0, in, in_pending);
+      if (rhs_multiplier == 0) launch_tile<OP_STAGE1>(s, a);
+      else launch_tile<OP_STAGE2>(s, a);
+    }
     ++s->stage_launches;
   }
   CU(cudaGetLastError());
   s->slot_buf[np1_qdp] = outb;
   s->slot_pending[np1_qdp] = 1;
-
-  // DSS of the extra level field (prim_advection_mod.F90:913-919, 943-958)
-  double** f = DSSopt == TSE_DSS_ETA ? &s->eta_dot : DSSopt == TSE_DSS_OMEGA ? &s->omega_p : DSSopt == TSE_DSS_DIV_VDP_AVE ? &s->divdp_proj : nullptr;
-  if (DSSopt != TSE_DSS_NO_VAR && !f) return fail("tse_euler_step: DSSopt=%d", DSSopt);
-  if (f) {
-    k_dss_level<<<level_blocks(s), 128, 0, s->stream>>>(s->geo, *f, nullptr, s->lev_tmp);
-    ++s->launches;
-    CU(cudaGetLastError());
-    std::swap(*f, s->lev_tmp);
-  }
-  return 0;
+  if (exchange_tracer(s, outb)) return 1;  // the bndry_exchangeV of the stage (:923-927); the unpack happens in the next reader
+  return dss_level_field(s, DSSopt);
 }
 
 int tse_qdp_time_avg(tse_handle s, int rkstage, int n0_qdp, int np1_qdp) {
   if (check_tl(np1_qdp) || check_tl(n0_qdp) || n0_qdp == np1_qdp) return fail("tse_qdp_time_avg: bad time levels %d %d", n0_qdp, np1_qdp);
   if (resolve_slot(s, n0_qdp)) return 1;
   const int in = s->slot_buf[np1_qdp], q0 = s->slot_buf[n0_qdp];
-  const int outb = pick_buffer(s, {in, q0});
-  if (s->use_tiled) {
-    TileArgs a = tile_args(s);
-    a.src[0] = s->qbuf[q0]; a.pending[0] = 0;
-    a.src[1] = s->qbuf[in]; a.pending[1] = s->slot_pending[np1_qdp];
-    a.out = s->qbuf[outb];
-    a.rkstage = (double)rkstage;
-    launch_tile<OP_TIME_AVG>(s, a);
-  } else
-  k_time_avg<<<plane_grid(s), GPL * QPB, 0, s->stream>>>(s->geo, view(s, in, s->slot_pending[np1_qdp]), s->qbuf[q0], (double)rkstage,
-                                                         s->qbuf[outb]);
-  if (!s->use_tiled) ++s->launches;
+  const int outb = pick_buffer({in, q0});
+  TileArgs a = tile_args(s);
+  set_src(s, a, 0, q0, 0);
+  set_src(s, a, 1, in, s->slot_pending[np1_qdp]);
+  a.out = s->qbuf[outb];
+  a.rkstage = (double)rkstage;
+  launch_tile<OP_TIME_AVG>(s, a);
   CU(cudaGetLastError());
   s->slot_buf[np1_qdp] = outb;
   s->slot_pending[np1_qdp] = 0;
@@ -818,6 +882,8 @@ int tse_diag_mass(tse_handle s, int tl, double* mass) {
   CU(cudaMemsetAsync(s->d_acc, 0, sizeof(long long) * 2 * Q, s->stream));
   k_mass_max<<<plane_grid(s), GPL * QPB, 0, s->stream>>>(s->geo, v, s->d_maxbits);
   ++s->launches;
+  // doubles >= 0 order like their bit patterns: the global max is an integer max
+  if (s->comm) NC(ncclAllReduce(s->d_maxbits, s->d_maxbits, Q, ncclUint64, ncclMax, s->comm, s->stream));
   std::vector<unsigned long long> mb(Q);
   CU(cudaMemcpyAsync(mb.data(), s->d_maxbits, sizeof(unsigned long long) * Q, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
@@ -830,6 +896,7 @@ int tse_diag_mass(tse_handle s, int tl, double* mass) {
   CU(cudaMemcpyAsync(s->d_shift, shift.data(), sizeof(int) * Q, cudaMemcpyHostToDevice, s->stream));
   k_mass_fixed<<<plane_grid(s), GPL * QPB, 0, s->stream>>>(s->geo, v, s->d_shift, s->d_acc);
   ++s->launches;
+  if (s->comm) NC(ncclAllReduce(s->d_acc, s->d_acc, 2 * Q, ncclInt64, ncclSum, s->comm, s->stream));
   std::vector<long long> acc(2 * Q);
   CU(cudaMemcpyAsync(acc.data(), s->d_acc, sizeof(long long) * 2 * Q, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
@@ -846,8 +913,15 @@ double tse_timer_ms(tse_handle s, const char* name) {
   auto it = s->timers.find(name);
   return it == s->timers.end() ? -1.0 : it->second;
 }
+int tse_timer_reset(tse_handle s) {
+  resolve_timers(s);
+  s->timers.clear();
+  return 0;
+}
 long long tse_launch_count(tse_handle s) { return s->launches; }
 long long tse_stage_launch_count(tse_handle s) { return s->stage_launches; }
+long long tse_device_bytes(tse_handle s) { return s->dev_bytes; }
+long long tse_halo_bytes(tse_handle s) { return s->halo_bytes; }
 
 int tse_mark(tse_handle s, int slot) {
   if (slot < 0 || slot >= 16) return fail("tse_mark: slot %d", slot);
@@ -862,15 +936,5 @@ double tse_mark_elapsed_ms(tse_handle s, int a, int b) {
   if (cudaEventElapsedTime(&ms, s->marks[a], s->marks[b]) != cudaSuccess) return -1.0;
   return ms;
 }
-int tse_timer_reset(tse_handle s) {
-  resolve_timers(s);
-  s->timers.clear();
-  return 0;
-}
-int tse_get_wind(tse_handle s, double* vn0, long long s_vn0, double* dp, long long s_dp) {
-  if (level_copy(s, s->vn0, vn0, s_vn0, 2, NLEV, 0)) return 1;
-  return level_copy(s, s->dp, dp, s_dp, 1, NLEV, 0);
-}
-long long tse_device_bytes(tse_handle s) { return s->dev_bytes; }
 
 }  // extern "C"

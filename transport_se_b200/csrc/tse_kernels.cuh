@@ -1,10 +1,9 @@
-// CUDA kernels of the tracer-advection path (sm_100a, FP64).
+// CUDA kernels of the tracer-advection path (sm_100a, FP64): level-field kernels, halo packing, layout conversion and the
+// plane-per-thread view used by the diagnostics.  The tracer-field stage kernels live in tse_tile.cuh.
 //
-// Work decomposition: one thread owns one 4x4 plane (element, level, tracer); a CTA covers
-// (group of 16 elements, chunk of 4 levels) x QPB tracers, i.e. QPB contiguous 8 KB tiles of the
-// tracer field.  The DSS (edgeVpack / bndry_exchangeV / edgeVunpack, edge_mod.F90:366-742) is never
-// materialised as an edge buffer: a kernel that consumes a field produced "pre-DSS" gathers the
-// neighbour nodes in the reference's unpack order while loading (see DssView::resolve).
+// The DSS (edgeVpack / bndry_exchangeV / edgeVunpack, edge_mod.F90:366-742) is never materialised as an edge buffer:
+// a kernel that consumes a field produced "pre-DSS" gathers the neighbour nodes in the reference's unpack order while
+// loading (DssView::load here, the shared-memory tile + halo in tse_tile.cuh).
 #pragma once
 #include "tse_ops.cuh"
 
@@ -15,7 +14,6 @@ constexpr int QPB = 4;  // tracers per CTA in the plane-per-thread kernels
 struct Geo {
   const double* spheremp;   // [e][16]
   const double* rspheremp;  // [e][16]
-  const double* rmp;        // 1/spheremp
   const double* rmr;        // rmetdet*rrearth
   const double* mD;         // [e][4][16]: metdet*Dinv(1,1), (1,2), (2,1), (2,2)
   const double* T;          // [e][3][16]: spheremp*rrearth^2*(Dinv Dinv^T) 11,12,22
@@ -62,11 +60,6 @@ struct DssView {
     for (int n = 0; n < 16; ++n) v[n] = rs[n] * v[n];
   }
 };
-
-// Per-(element, level) stage package written by k_stage_prep: 5 planes per level plane.
-//   0: U1   1: U2   2: rdp = 1/dp_s   3: c = spheremp*dp_star   4: rdpstar = 1/dp_star
-// dp_s = derived%dp - rhs_multiplier*dt*divdp_proj (prim_advection_mod.F90:753,847), dp_star = dp_s - dt*divdp (:864)
-constexpr int NPKG = 5;
 
 struct ThreadPlane {
   int e, q, k;
@@ -119,46 +112,6 @@ __global__ void __launch_bounds__(128) k_divdp(Geo G, Dvv D, const double* __res
   store16(divdp_proj + lp, r);
 }
 
-// stage package (see NPKG)
-__global__ void __launch_bounds__(128) k_stage_prep(Geo G, const double* __restrict__ vn0, const double* __restrict__ dp,
-                                                    const double* __restrict__ divdp, const double* __restrict__ divdp_proj,
-                                                    double rhs_mult_dt, double dt, double* __restrict__ pkg, size_t pkg_stride) {
-  int e, k;
-  if (!thread_level(G, e, k)) return;
-  const size_t lp = lplane(e, k) * 16;
-  double v1[16], v2[16], d[16], dd[16], dj[16];
-  load16(vn0 + vplane(e, k, 0) * 16, v1);
-  load16(vn0 + vplane(e, k, 1) * 16, v2);
-  load16(dp + lp, d);
-  load16(divdp + lp, dd);
-  load16(divdp_proj + lp, dj);
-  const double* mD = G.mD + (size_t)e * 64;
-  const double* sp = G.spheremp + (size_t)e * 16;
-  double o[16];
-  double rdp[16], dps[16];
-  TSE_UNROLL
-  for (int n = 0; n < 16; ++n) {
-    const double dp_s = d[n] - rhs_mult_dt * dj[n];
-    rdp[n] = 1.0 / dp_s;
-    dps[n] = dp_s - dt * dd[n];
-    v1[n] = v1[n] * rdp[n];  // Vstar
-    v2[n] = v2[n] * rdp[n];
-  }
-  TSE_UNROLL
-  for (int n = 0; n < 16; ++n) o[n] = mD[n] * v1[n] + mD[16 + n] * v2[n];
-  store16(pkg + 0 * pkg_stride + lp, o);
-  TSE_UNROLL
-  for (int n = 0; n < 16; ++n) o[n] = mD[32 + n] * v1[n] + mD[48 + n] * v2[n];
-  store16(pkg + 1 * pkg_stride + lp, o);
-  store16(pkg + 2 * pkg_stride + lp, rdp);
-  TSE_UNROLL
-  for (int n = 0; n < 16; ++n) o[n] = sp[n] * dps[n];
-  store16(pkg + 3 * pkg_stride + lp, o);
-  TSE_UNROLL
-  for (int n = 0; n < 16; ++n) o[n] = 1.0 / dps[n];
-  store16(pkg + 4 * pkg_stride + lp, o);
-}
-
 // DSS of one level field (the DSSopt variable of euler_step, prim_advection_mod.F90:913-919,943-958):
 // out = rspheremp * sum_{sharing elements} spheremp*f, in unpack order.  ghost: [slot][k] = spheremp*f of off-GPU nodes.
 __global__ void __launch_bounds__(128) k_dss_level(Geo G, const double* __restrict__ f, const double* __restrict__ ghost,
@@ -199,187 +152,40 @@ __global__ void __launch_bounds__(128) k_dss_level(Geo G, const double* __restri
 // ---------------------------------------------------------------------------------------------
 // tracer-field kernels (one thread per (element, level, tracer) plane)
 // ---------------------------------------------------------------------------------------------
-struct MinMaxIO {
-  double* qmin;            // [plane] limiter bounds, in/out (prim_advection_mod.F90:461 qmin/qmax(nlev,qsize,nelemd))
-  double* qmax;
-  double* qmin_loc;        // [plane] element-local extrema written before a neighbour exchange
-  double* qmax_loc;
-  const double* ghost_mm;  // [bundle][2][q][k] extrema of off-GPU neighbour elements
-};
-
-// element-local min/max of Q = Qdp/dp (prim_advection_mod.F90:764-775): feeds neighbor_minmax
-__global__ void __launch_bounds__(GPL* QPB) k_minmax_local(Geo G, DssView in, const double* __restrict__ pkg, size_t pkg_stride,
-                                                           MinMaxIO mm) {
-  const ThreadPlane t = thread_plane(G, in.Q);
-  if (!t.valid) return;
-  double v[16], rdp[16];
-  in.load(G, t.e, t.q, t.k, v);
-  load16(pkg + 2 * pkg_stride + lplane(t.e, t.k) * 16, rdp);
-  double mn = v[0] * rdp[0], mx = mn;
-  TSE_UNROLL
-  for (int n = 1; n < 16; ++n) {
-    const double qv = v[n] * rdp[n];
-    mn = fmin(mn, qv);
-    mx = fmax(mx, qv);
-  }
-  const size_t p = qplane(t.e, t.q, t.k, in.Q);
-  mm.qmin_loc[p] = mn;
-  mm.qmax_loc[p] = mx;
+// ---------------------------------------------------------------------------------------------
+// halo packing for the multi-GPU exchange (the send side of bndry_exchangeV, bndry_mod.F90:74-112): the boundary nodes
+// that the reference's edgeVpack would place in the slab of a neighbour rank, gathered into a contiguous send buffer
+// with the layout of the receiver's ghost array.
+// ---------------------------------------------------------------------------------------------
+// tracer field: send[(i*Q + q)*NLEV + k] = field(elem(i), q, k, node(i))
+__global__ void __launch_bounds__(256) k_pack_tracer(const double* __restrict__ f, const int* __restrict__ send_src, int nsend, int Q,
+                                                     double* __restrict__ send) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)nsend * Q * NLEV;
+  if (idx >= total) return;
+  const int k = idx % NLEV, q = (idx / NLEV) % Q, i = idx / ((size_t)NLEV * Q);
+  const int code = send_src[i];
+  send[idx] = f[qplane(code >> 4, q, k, Q) * 16 + (code & 15)];
 }
-
-// min/max over the element and its (up to 8) neighbours: neighbor_minmax, viscosity_mod.F90:748-816
-__device__ __forceinline__ void neighbor_minmax(const Geo& G, const MinMaxIO& mm, int e, int q, int k, int Q, double& mn, double& mx) {
-  const size_t p = qplane(e, q, k, Q);
-  mn = mm.qmin_loc[p];
-  mx = mm.qmax_loc[p];
-  const int* nb = G.nbr8 + (size_t)e * 8;
-  TSE_UNROLL
-  for (int d = 0; d < 8; ++d) {
-    const int b = nb[d];
-    if (b >= 0) {
-      const size_t pb = qplane(b, q, k, Q);
-      mn = fmin(mn, mm.qmin_loc[pb]);
-      mx = fmax(mx, mm.qmax_loc[pb]);
-    } else if (b <= -2) {
-      const size_t gb = ((size_t)(-b - 2) * 2 * Q + q) * NLEV + k;
-      mn = fmin(mn, mm.ghost_mm[gb]);
-      mx = fmax(mx, mm.ghost_mm[gb + (size_t)Q * NLEV]);
-    }
-  }
+// level field (mass weighted, as edgeVpack sees it after "DSSvar = spheremp*DSSvar"): send[i*NLEV + k]
+__global__ void __launch_bounds__(256) k_pack_level(const double* __restrict__ f, const double* __restrict__ spheremp,
+                                                    const int* __restrict__ send_src, int nsend, double* __restrict__ send) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)nsend * NLEV) return;
+  const int k = idx % NLEV, i = idx / NLEV;
+  const int code = send_src[i], e = code >> 4, nd = code & 15;
+  send[idx] = spheremp[(size_t)e * 16 + nd] * f[lplane(e, k) * 16 + nd];
 }
-
-// first half of biharmonic_wk_scalar_minmax (viscosity_mod.F90:353-405): Q = Qdp/dp, local extrema, qtens = laplace_sphere_wk(Q)
-__global__ void __launch_bounds__(GPL* QPB) k_biharm_pre(Geo G, Dvv D, DssView in, const double* __restrict__ pkg, size_t pkg_stride,
-                                                         MinMaxIO mm, double* __restrict__ qtens) {
-  const ThreadPlane t = thread_plane(G, in.Q);
-  if (!t.valid) return;
-  double v[16], lap[16];
-  in.load(G, t.e, t.q, t.k, v);
-  {
-    double rdp[16];
-    load16(pkg + 2 * pkg_stride + lplane(t.e, t.k) * 16, rdp);
-    TSE_UNROLL
-    for (int n = 0; n < 16; ++n) v[n] = v[n] * rdp[n];
-  }
-  double mn = v[0], mx = v[0];
-  TSE_UNROLL
-  for (int n = 1; n < 16; ++n) {
-    mn = fmin(mn, v[n]);
-    mx = fmax(mx, v[n]);
-  }
-  const size_t p = qplane(t.e, t.q, t.k, in.Q);
-  mm.qmin_loc[p] = mn;
-  mm.qmax_loc[p] = mx;
-  const double* T = G.T + (size_t)t.e * 48;
-  laplace_wk(v, D, T, T + 16, T + 32, lap);
-  store16(qtens + p * 16, lap);
-}
-
-// One RK stage of euler_step (prim_advection_mod.F90:667-970) for rhs_multiplier = MODE-1.
-//   MODE 1: bounds = neighbor_minmax of the pre-computed local extrema
-//   MODE 2: bounds = min/max(stored bounds, local extrema of the DSS'd input)        (:781-793)
-//   MODE 3: bounds = neighbour extrema; adds Qtens_biharmonic = -3*dt*nu_q*dp0(k)*lap(rspheremp*DSS(qtens))/spheremp (:796-827)
-// Output: Qdp(np1) = spheremp*limited(Qtens), still to be DSS'd (the consumer gathers).
-struct StageArgs {
-  DssView in;
-  DssView qtens;  // MODE 3 only
-  const double* pkg;
-  size_t pkg_stride;
-  MinMaxIO mm;
-  double* out;
-  double dt;
-  double visc_coef;  // -rhs_viss*dt*nu_q
-  const double* dp0; // [NLEV] (hyai(k+1)-hyai(k))*ps0 + (hybi(k+1)-hybi(k))*ps0
-};
-
-template <int MODE>
-__global__ void __launch_bounds__(GPL* QPB) k_euler_stage(Geo G, Dvv D, StageArgs a) {
-  const int Q = a.in.Q;
-  const ThreadPlane t = thread_plane(G, Q);
-  if (!t.valid) return;
-  const size_t p = qplane(t.e, t.q, t.k, Q);
-  const size_t lp = lplane(t.e, t.k) * 16;
-  double v[16];
-  a.in.load(G, t.e, t.q, t.k, v);
-
-  double minp, maxp;
-  if (MODE == 2) {
-    double rdp[16];
-    load16(a.pkg + 2 * a.pkg_stride + lp, rdp);
-    double mn = v[0] * rdp[0], mx = mn;
-    TSE_UNROLL
-    for (int n = 1; n < 16; ++n) {
-      const double qv = v[n] * rdp[n];
-      mn = fmin(mn, qv);
-      mx = fmax(mx, qv);
-    }
-    minp = fmin(a.mm.qmin[p], mn);
-    maxp = fmax(a.mm.qmax[p], mx);
-  } else {
-    neighbor_minmax(G, a.mm, t.e, t.q, t.k, Q, minp, maxp);
-  }
-
-  double x[16];
-  {
-    double g1[16], g2[16];
-    {
-      double u[16];
-      load16(a.pkg + lp, u);
-      TSE_UNROLL
-      for (int n = 0; n < 16; ++n) g1[n] = u[n] * v[n];
-      load16(a.pkg + a.pkg_stride + lp, u);
-      TSE_UNROLL
-      for (int n = 0; n < 16; ++n) g2[n] = u[n] * v[n];
-    }
-    div_contract(g1, g2, D, x);
-    const double* rmr = G.rmr + (size_t)t.e * 16;
-    TSE_UNROLL
-    for (int n = 0; n < 16; ++n) x[n] = fma(-a.dt, x[n] * rmr[n], v[n]);  // Qtens = Qdp - dt*div
-  }
-  if (MODE == 3) {
-    double s[16], lap[16];
-    a.qtens.load(G, t.e, t.q, t.k, s);  // rspheremp * DSS(lap(Q))
-    const double* T = G.T + (size_t)t.e * 48;
-    laplace_wk(s, D, T, T + 16, T + 32, lap);
-    const double cf = a.visc_coef * a.dp0[t.k];
-    const double* rmp = G.rmp + (size_t)t.e * 16;
-    TSE_UNROLL
-    for (int n = 0; n < 16; ++n) x[n] = x[n] + cf * lap[n] * rmp[n];
-  }
-  {
-    double c[16], rd[16];
-    load16(a.pkg + 3 * a.pkg_stride + lp, c);
-    load16(a.pkg + 4 * a.pkg_stride + lp, rd);
-    limiter_optim_iter_full(x, c, rd, minp, maxp);
-    TSE_UNROLL
-    for (int n = 0; n < 16; ++n) x[n] = x[n] * c[n];  // spheremp * (x*dpmass)
-  }
-  store16(a.out + p * 16, x);
-  a.mm.qmin[p] = minp;
-  a.mm.qmax[p] = maxp;
-}
-
-// qdp_time_avg (prim_advection_mod.F90:645-662) fused with the pending DSS of the last stage
-__global__ void __launch_bounds__(GPL* QPB) k_time_avg(Geo G, DssView np1, const double* __restrict__ q0, double rkstage,
-                                                       double* __restrict__ out) {
-  const ThreadPlane t = thread_plane(G, np1.Q);
-  if (!t.valid) return;
-  double v[16], w[16];
-  np1.load(G, t.e, t.q, t.k, v);
-  const size_t p = qplane(t.e, t.q, t.k, np1.Q) * 16;
-  load16(q0 + p, w);
-  TSE_UNROLL
-  for (int n = 0; n < 16; ++n) v[n] = (w[n] + (rkstage - 1.0) * v[n]) / rkstage;
-  store16(out + p, v);
-}
-
-// materialise a pending DSS (needed only when the host asks for the field or before the remap)
-__global__ void __launch_bounds__(GPL* QPB) k_resolve(Geo G, DssView in, double* __restrict__ out) {
-  const ThreadPlane t = thread_plane(G, in.Q);
-  if (!t.valid) return;
-  double v[16];
-  in.load(G, t.e, t.q, t.k, v);
-  store16(out + qplane(t.e, t.q, t.k, in.Q) * 16, v);
+// element extrema for neighbor_minmax: send[((b*2 + {0,1})*Q + q)*NLEV + k] = qmin_loc / qmax_loc of element mm_elem(b)
+__global__ void __launch_bounds__(256) k_pack_minmax(const double* __restrict__ lmin, const double* __restrict__ lmax,
+                                                     const int* __restrict__ mm_elem, int nb, int Q, double* __restrict__ send) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)nb * Q * NLEV;
+  if (idx >= total) return;
+  const int k = idx % NLEV, q = (idx / NLEV) % Q, b = idx / ((size_t)NLEV * Q);
+  const size_t p = qplane(mm_elem[b], q, k, Q);
+  send[((size_t)(b * 2) * Q + q) * NLEV + k] = lmin[p];
+  send[((size_t)(b * 2 + 1) * Q + q) * NLEV + k] = lmax[p];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -555,8 +555,8 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
         flux_div(S, pp + cfg.U1 * PP_BYTES, pp + cfg.U2 * PP_BYTES, pl, D, y);
 #endif
         asm volatile("" ::: "memory");
-        const unsigned e1a = smem_u32 + (unsigned)(elb - smem) + cfg.E1 * EL_BYTES + el * 16;
-        const unsigned e2a = smem_u32 + (unsigned)(elb - smem) + cfg.E2 * EL_BYTES + el * 16;
+        const unsigned e1a = smem_u32 + (unsigned)(elb - smem) + (cfg.E1 < 0 ? 0 : cfg.E1) * EL_BYTES + el * 16;
+        const unsigned e2a = smem_u32 + (unsigned)(elb - smem) + (cfg.E2 < 0 ? 0 : cfg.E2) * EL_BYTES + el * 16;
         TSE_UNROLL
         for (int c = 0; c < 8; ++c) {
           const double2 e1 = lds128v(e1a + c * GE * 16);
@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
         }
         asm volatile("" ::: "memory");
 #ifndef TSE_SKIP_LIMITER
-        limiter_y(y, smem_u32 + (unsigned)(pp - smem) + cfg.CL * PP_BYTES + pl * 16, sumc, minp, maxp);
+        limiter_y(y, smem_u32 + (unsigned)(pp - smem) + (cfg.CL < 0 ? 0 : cfg.CL) * PP_BYTES + pl * 16, sumc, minp, maxp);
 #endif
         asm volatile("" ::: "memory");
         a.qmin[pidx] = minp;
