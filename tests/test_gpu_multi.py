@@ -10,17 +10,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _ngpu():
-    try:
-        import torch
-        return torch.cuda.device_count()
-    except Exception:
-        return 0
+    from transport_se_b200.advection import cuda_lib
+    return cuda_lib().tse_device_count()
 
 
 @pytest.mark.parametrize("nranks,ne,test", [(2, 8, 11), (2, 8, 12), (4, 8, 11), (8, 30, 11)])
 def test_bit_for_bit_across_gpu_counts(nranks, ne, test):
-    if _ngpu() < nranks:
-        pytest.skip("needs %d GPUs" % nranks)
+    n = _ngpu()
+    if n < nranks:
+        pytest.skip("needs %d GPUs, this box has %d" % (nranks, n))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks), "--master-addr", "127.0.0.1",
            "--master-port", str(29500 + nranks + ne), os.path.join(ROOT, "tests", "mgpu_check.py"), str(ne), "5", str(test), "2"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
