@@ -287,6 +287,10 @@ def run_ours(args):
 
 
 def main():
+    # libraries (NCCL, torchrun) may write to stdout: keep fd 1 for the single JSON line, send everything else to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=16)
@@ -303,6 +307,7 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

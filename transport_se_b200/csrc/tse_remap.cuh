@@ -13,7 +13,8 @@ namespace tse {
 constexpr int RM_KL = 32;                 // level lanes
 constexpr int RM_THREADS = 16 * RM_KL;    // 512
 constexpr int RM_R = 3;                   // levels owned per thread: j = kl + 32 r, j in 0..73
-constexpr int RM_ROWS = 76 + 73 + 76 + 74 + 73 + 3 * 72 + 73;
+constexpr int RM_ROWS = 76 + 73 + 76 + 74 + 73 + 3 * 72 + 73 + 73 + 8;
+constexpr int RM_SEG = 9;                 // the prefix sum over 72 levels runs as 8 segments of 9 levels
 constexpr size_t RM_SMEM = (size_t)RM_ROWS * 16 * sizeof(double);
 
 struct RemapArgs {
@@ -34,12 +35,14 @@ struct RemapArgs {
 __global__ void __launch_bounds__(RM_THREADS, 1) k_vertical_remap(RemapArgs a) {
   extern __shared__ double sm[];
   double(*s_dpo)[16] = reinterpret_cast<double(*)[16]>(sm);  // row j+1, j=-1..74
-  double(*s_araw)[16] = s_dpo + 76;                          // row k, k=0..72 (later massn2)
+  double(*s_araw)[16] = s_dpo + 76;                          // row k, k=0..72
   double(*s_ao)[16] = s_araw + 73;                           // row j+1
   double(*s_dma)[16] = s_ao + 76;                            // row j, j=0..73   (phase A: pio[0..73])
   double(*s_ai)[16] = s_dma + 74;                            // row j, j=0..72   (phase A: pin[0..72])
   double(*s_coef)[16] = s_ai + 73;                           // row c*72 + (j-1)
   double(*s_masso)[16] = s_coef + 216;                       // row k, k=0..72
+  double(*s_m2)[16] = s_masso + 73;                          // row k, k=0..72: massn2
+  double(*s_seg)[16] = s_m2 + 73;                            // row s, s=0..7: segment totals of the prefix sum
   double(*s_pio)[16] = s_dma;
   double(*s_pin)[16] = s_ai;
 
@@ -123,32 +126,54 @@ __global__ void __launch_bounds__(RM_THREADS, 1) k_vertical_remap(RemapArgs a) {
   __syncthreads();  // pio/pin storage is reused as dma/ai below
 
   // ---- phase B: tracers -----------------------------------------------------------------
+  // The next tracer's column is prefetched into registers while the current one is processed.
+  double nxt[RM_R];
+#pragma unroll
+  for (int r = 0; r < RM_R; ++r) {
+    const int j = kl + RM_KL * r;
+    nxt[r] = (j >= 1 && j <= NLEV) ? a.q[qplane(e, 0, j - 1, a.Q) * 16 + n] : 0.0;
+  }
+  const int sg = threadIdx.x >> 4;  // prefix-sum segment handled by threads 0..127 (column n, segment sg)
   for (int q = 0; q < a.Q; ++q) {
 #pragma unroll
     for (int r = 0; r < RM_R; ++r) {
       const int j = kl + RM_KL * r;
       if (j >= 1 && j <= NLEV) {
-        const double v = a.q[qplane(e, q, j - 1, a.Q) * 16 + n];
-        s_araw[j][n] = v;
-        s_ao[j + 1][n] = v * rdpo[r];  // ao = Qdp/dpo (:187)
+        s_araw[j][n] = nxt[r];
+        s_ao[j + 1][n] = nxt[r] * rdpo[r];  // ao = Qdp/dpo (:187)
+      }
+    }
+    if (q + 1 < a.Q) {
+#pragma unroll
+      for (int r = 0; r < RM_R; ++r) {
+        const int j = kl + RM_KL * r;
+        if (j >= 1 && j <= NLEV) nxt[r] = a.q[qplane(e, q + 1, j - 1, a.Q) * 16 + n];
       }
     }
     __syncthreads();
-    if (kl == 0) {  // masso prefix sum (:184-186), sequential order
-      double m = 0.0;
-      s_masso[0][n] = 0.0;
-#pragma unroll 8
-      for (int k = 1; k <= NLEV; ++k) {
-        m += s_araw[k][n];
-        s_masso[k][n] = m;
-      }
-    } else if (kl == 1) {  // mirrored ghost cells (:193-196)
+    // masso prefix sum (:184-186) as 8 segments of 9 levels: segment totals, then offsets (fixed order, deterministic)
+    if (sg < 8) {
+      double t = 0.0;
+#pragma unroll
+      for (int i = 1; i <= RM_SEG; ++i) t += s_araw[sg * RM_SEG + i][n];
+      s_seg[sg][n] = t;
+    } else if (sg == 8) {  // mirrored ghost cells (:193-196)
       s_ao[0][n] = s_ao[3][n];
       s_ao[1][n] = s_ao[2][n];
       s_ao[74][n] = s_ao[73][n];
       s_ao[75][n] = s_ao[72][n];
     }
     __syncthreads();
+    if (sg < 8) {
+      double m = 0.0;
+      for (int i = 0; i < sg; ++i) m += s_seg[i][n];
+      if (sg == 0) s_masso[0][n] = 0.0;
+#pragma unroll
+      for (int i = 1; i <= RM_SEG; ++i) {
+        m += s_araw[sg * RM_SEG + i][n];
+        s_masso[sg * RM_SEG + i][n] = m;
+      }
+    }
     // compute_ppm (:267-342): dma
 #pragma unroll
     for (int r = 0; r < RM_R; ++r) {
@@ -200,18 +225,18 @@ __global__ void __launch_bounds__(RM_THREADS, 1) k_vertical_remap(RemapArgs a) {
         const double x1 = -0.5, x2 = z2[r];
         const double c0 = s_coef[kk - 1][n], c1 = s_coef[72 + kk - 1][n], c2 = s_coef[144 + kk - 1][n];
         const double integ = c0 * (x2 - x1) + c1 * (x2 * x2 - x1 * x1) / 0.2e1 + c2 * (x2 * x2 * x2 - x1 * x1 * x1) / 0.3e1;
-        s_araw[j][n] = s_masso[kk - 1][n] + integ * s_dpo[kk + 1][n];
+        s_m2[j][n] = s_masso[kk - 1][n] + integ * s_dpo[kk + 1][n];
       } else if (j == 0) {
-        s_araw[0][n] = 0.0;
+        s_m2[0][n] = 0.0;
       }
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < RM_R; ++r) {
       const int j = kl + RM_KL * r;
-      if (j >= 1 && j <= NLEV) a.q[qplane(e, q, j - 1, a.Q) * 16 + n] = s_araw[j][n] - s_araw[j - 1][n];
+      if (j >= 1 && j <= NLEV) a.q[qplane(e, q, j - 1, a.Q) * 16 + n] = s_m2[j][n] - s_m2[j - 1][n];
     }
-    __syncthreads();
+    // no barrier needed here: the next iteration first writes s_araw/s_ao, whose last readers sit before the previous barrier
   }
 }
 
