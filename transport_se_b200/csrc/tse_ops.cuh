@@ -29,6 +29,11 @@ struct Dvv {
 
 #define TSE_UNROLL _Pragma("unroll")
 
+// min/max as compare+select (DSETP + SEL).  fmin/fmax expand to ~8 instructions on sm_100a (NaN-quieting sequence);
+// NaNs do not occur on this path, and for ordinary numbers the results are identical.
+__device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }
+__device__ __forceinline__ double dmax(double a, double b) { return b > a ? b : a; }
+
 // r(a,b) = sum_i Dvv(i,a) g1(i,b) + sum_i Dvv(i,b) g2(a,i)      [div(l,j) + vvtemp(j,l) of divergence_sphere]
 __device__ __forceinline__ void div_contract(const double (&g1)[16], const double (&g2)[16], const Dvv& D, double (&r)[16]) {
   TSE_UNROLL

@@ -6,7 +6,7 @@
 // kept in registers of the thread that owns the level; the tracer loop then runs level-parallel through
 // shared memory (the PPM stencils are local in k).  The only serial pieces are the prefix sums.
 #pragma once
-#include "tse_layout.cuh"
+#include "tse_ops.cuh"
 
 namespace tse {
 
@@ -128,27 +128,30 @@ __global__ void __launch_bounds__(RM_THREADS, 1) k_vertical_remap(RemapArgs a) {
   // ---- phase B: tracers -----------------------------------------------------------------
   // The next tracer's column is prefetched into registers while the current one is processed.
   double nxt[RM_R];
+  size_t goff[RM_R];   // offset of (e, tracer 0, level j-1, node n); consecutive tracers are GPL*16 doubles apart
+  bool own[RM_R];      // this thread owns level j = kl + 32 r in 1..72
 #pragma unroll
   for (int r = 0; r < RM_R; ++r) {
     const int j = kl + RM_KL * r;
-    nxt[r] = (j >= 1 && j <= NLEV) ? a.q[qplane(e, 0, j - 1, a.Q) * 16 + n] : 0.0;
+    own[r] = (j >= 1 && j <= NLEV);
+    goff[r] = own[r] ? qplane(e, 0, j - 1, a.Q) * 16 + n : 0;
+    nxt[r] = own[r] ? a.q[goff[r]] : 0.0;
   }
+  const double third = 1.0 / 3.0, sixth = 1.0 / 6.0;
   const int sg = threadIdx.x >> 4;  // prefix-sum segment handled by threads 0..127 (column n, segment sg)
   for (int q = 0; q < a.Q; ++q) {
 #pragma unroll
     for (int r = 0; r < RM_R; ++r) {
       const int j = kl + RM_KL * r;
-      if (j >= 1 && j <= NLEV) {
+      if (own[r]) {
         s_araw[j][n] = nxt[r];
         s_ao[j + 1][n] = nxt[r] * rdpo[r];  // ao = Qdp/dpo (:187)
       }
     }
     if (q + 1 < a.Q) {
 #pragma unroll
-      for (int r = 0; r < RM_R; ++r) {
-        const int j = kl + RM_KL * r;
-        if (j >= 1 && j <= NLEV) nxt[r] = a.q[qplane(e, q + 1, j - 1, a.Q) * 16 + n];
-      }
+      for (int r = 0; r < RM_R; ++r)
+        if (own[r]) nxt[r] = a.q[goff[r] + (size_t)(q + 1) * (GPL * 16)];
     }
     __syncthreads();
     // masso prefix sum (:184-186) as 8 segments of 9 levels: segment totals, then offsets (fixed order, deterministic)
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) k_vertical_remap(RemapArgs a) {
       if (j <= NLEV + 1) {
         const double am = s_ao[j][n], a0 = s_ao[j + 1][n], ap = s_ao[j + 2][n];
         const double da = px[r][0] * (px[r][1] * (ap - a0) + px[r][2] * (a0 - am));
-        double d = fmin(fabs(da), fmin(2. * fabs(a0 - am), 2. * fabs(ap - a0)));
+        double d = dmin(fabs(da), dmin(2. * fabs(a0 - am), 2. * fabs(ap - a0)));
         d = copysign(d, da);
         if ((ap - a0) * (a0 - am) <= 0.) d = 0.;
         s_dma[j][n] = d;
@@ -201,16 +204,17 @@ __global__ void __launch_bounds__(RM_THREADS, 1) k_vertical_remap(RemapArgs a) {
 #pragma unroll
     for (int r = 0; r < RM_R; ++r) {
       const int j = kl + RM_KL * r;
-      if (j >= 1 && j <= NLEV) {
+      if (own[r]) {
         const double aj = s_ao[j + 1][n];
         double al = s_ai[j - 1][n], ar = s_ai[j][n];
         if ((ar - aj) * (aj - al) <= 0.) {
           al = aj;
           ar = aj;
         }
-        if ((ar - al) * (aj - (al + ar) / 2.) > (ar - al) * (ar - al) / 6.) al = 3. * aj - 2. * ar;
-        if ((ar - al) * (aj - (al + ar) / 2.) < -((ar - al) * (ar - al)) / 6.) ar = 3. * aj - 2. * al;
-        s_coef[j - 1][n] = 1.5 * aj - (al + ar) / 4.;
+        // the reference divides by 6 (:323-329); multiplying by the rounded reciprocal differs by <= 1 ulp
+        if ((ar - al) * (aj - (al + ar) * 0.5) > (ar - al) * (ar - al) * sixth) al = 3. * aj - 2. * ar;
+        if ((ar - al) * (aj - (al + ar) * 0.5) < -((ar - al) * (ar - al)) * sixth) ar = 3. * aj - 2. * al;
+        s_coef[j - 1][n] = 1.5 * aj - (al + ar) * 0.25;
         s_coef[72 + j - 1][n] = ar - al;
         s_coef[144 + j - 1][n] = -6. * aj + 3. * (al + ar);
       }
@@ -220,11 +224,11 @@ __global__ void __launch_bounds__(RM_THREADS, 1) k_vertical_remap(RemapArgs a) {
 #pragma unroll
     for (int r = 0; r < RM_R; ++r) {
       const int j = kl + RM_KL * r;
-      if (j >= 1 && j <= NLEV) {
+      if (own[r]) {
         const int kk = kid[r];
         const double x1 = -0.5, x2 = z2[r];
         const double c0 = s_coef[kk - 1][n], c1 = s_coef[72 + kk - 1][n], c2 = s_coef[144 + kk - 1][n];
-        const double integ = c0 * (x2 - x1) + c1 * (x2 * x2 - x1 * x1) / 0.2e1 + c2 * (x2 * x2 * x2 - x1 * x1 * x1) / 0.3e1;
+        const double integ = c0 * (x2 - x1) + c1 * (x2 * x2 - x1 * x1) * 0.5 + c2 * (x2 * x2 * x2 - x1 * x1 * x1) * third;
         s_m2[j][n] = s_masso[kk - 1][n] + integ * s_dpo[kk + 1][n];
       } else if (j == 0) {
         s_m2[0][n] = 0.0;
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(RM_THREADS, 1) k_vertical_remap(RemapArgs a) {
 #pragma unroll
     for (int r = 0; r < RM_R; ++r) {
       const int j = kl + RM_KL * r;
-      if (j >= 1 && j <= NLEV) a.q[qplane(e, q, j - 1, a.Q) * 16 + n] = s_m2[j][n] - s_m2[j - 1][n];
+      if (own[r]) a.q[goff[r] + (size_t)q * (GPL * 16)] = s_m2[j][n] - s_m2[j - 1][n];
     }
     // no barrier needed here: the next iteration first writes s_araw/s_ao, whose last readers sit before the previous barrier
   }

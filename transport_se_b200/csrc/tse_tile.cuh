@@ -78,8 +78,9 @@ __host__ __device__ constexpr TileCfg tile_cfg(int op) {
                              : TileCfg{0, 1, 1, -1, -1, -1, -1, -1, -1, 0, -1, -1, -1};
 }
 __host__ __device__ constexpr int tile_in_bytes(int hmax) { return TILE_BYTES + QI * hmax * KC * 8 + 16; }
+constexpr int NBUF = 2;  // IN buffers: two tiles are in flight while a third is being processed from registers
 __host__ __device__ constexpr int tile_smem_bytes(int op, int hmax) {
-  return tile_in_bytes(hmax) + (tile_cfg(op).has_out ? TILE_BYTES : 0) + tile_cfg(op).npp * PP_BYTES + tile_cfg(op).nel * EL_BYTES;
+  return NBUF * tile_in_bytes(hmax) + (tile_cfg(op).has_out ? TILE_BYTES : 0) + tile_cfg(op).npp * PP_BYTES + tile_cfg(op).nel * EL_BYTES;
 }
 
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
@@ -90,6 +91,7 @@ __device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;\n" ::); }
 
 __device__ __forceinline__ double2 lds128(const unsigned char* base, int off) { return *reinterpret_cast<const double2*>(base + off); }
 __device__ __forceinline__ double lds64(const unsigned char* base, int off) { return *reinterpret_cast<const double*>(base + off); }
@@ -134,7 +136,7 @@ __device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, doubl
       for (int u = 0; u < 4; ++u) {
         const int n = 2 * cc + u;
         const double hi = maxp * cv[u], lo = minp * cv[u];
-        const double tcl = fmin(fmax(y[n], lo), hi);
+        const double tcl = dmin(dmax(y[n], lo), hi);
         const double d = y[n] - tcl;  // (x-maxp)*c above, -(minp-x)*c below, 0 inside
         y[n] = tcl;
         if (u == 0) a0 += d;
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
   constexpr bool kHasOut = cfg.has_out != 0;
   extern __shared__ __align__(16) unsigned char smem[];
   const int IN_BYTES = tile_in_bytes(tb.hmax);
-  unsigned char* const outb = smem + IN_BYTES;
+  unsigned char* const outb = smem + NBUF * IN_BYTES;
   unsigned char* const pp = outb + (kHasOut ? TILE_BYTES : 0);
   unsigned char* const elb = pp + cfg.npp * PP_BYTES;
   const int ZERO_OFF = TILE_BYTES + QI * tb.hmax * KC * 8;
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
 
   // ---- level package -------------------------------------------------------------------------------------------
   const bool main_pending = (OP == OP_STAGE3) ? (a.pending[1] != 0) : (a.pending[0] != 0);
-  if (t == 0) *reinterpret_cast<double*>(smem + ZERO_OFF) = 0.0;
+  if (t < NBUF) *reinterpret_cast<double*>(smem + t * IN_BYTES + ZERO_OFF) = 0.0;
   if (cfg.nel > 0 && t < GE * 8) {
     // element-level fields: thread -> (element t>>3, nodes 2*(t&7), +1)
     const int pe = t >> 3, c = t & 7, ee = g * GE + pe;
@@ -390,14 +392,15 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
     const double* src = a.src[which];
     const int q0 = it * QI, nq = min(QI, Q - q0);
     const double* tsrc = src + cta_base + (size_t)q0 * GPL * 16 + t * 2;
+    const unsigned sb = smem_u32 + (j % NBUF) * IN_BYTES;
     // chunk i = r*TT + t -> plane r*TT/8 + (t>>3), 16-byte unit t&7: the swizzle term does not depend on r
     if (nq == QI) {
       TSE_UNROLL
-      for (int r = 0; r < 8; ++r) cp_async16(smem_u32 + cp_dst0 + r * (TT * 16), tsrc + r * (TT * 2));
+      for (int r = 0; r < 8; ++r) cp_async16(sb + cp_dst0 + r * (TT * 16), tsrc + r * (TT * 2));
     } else {
       TSE_UNROLL
       for (int r = 0; r < 8; ++r)
-        if (r * (TT / 8) + (t >> 3) < nq * GPL) cp_async16(smem_u32 + cp_dst0 + r * (TT * 16), tsrc + r * (TT * 2));
+        if (r * (TT / 8) + (t >> 3) < nq * GPL) cp_async16(sb + cp_dst0 + r * (TT * 16), tsrc + r * (TT * 2));
     }
     if (a.pending[which]) {
       TSE_UNROLL
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
           for (int qi2 = 0; qi2 < nq; ++qi2) {
             const double* gp = hsrc[r] >= 0 ? src + hsrc[r] + (size_t)(q0 + qi2) * GPL * 16
                                             : a.ghost[which] + (-(hsrc[r] + 1)) + (size_t)(q0 + qi2) * NLEV;
-            cp_async8(smem_u32 + hdst[r] + qi2 * tb.hmax * KC * 8, gp);
+            cp_async8(sb + hdst[r] + qi2 * tb.hmax * KC * 8, gp);
           }
         }
       }
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
         for (int qi2 = 0; qi2 < nq; ++qi2) {
           const double* gp = (code >= 0) ? src + (qplane(code >> 4, q0 + qi2, kq, Q) * 16 + (code & 15))
                                          : a.ghost[which] + ((size_t)(-code - 2) * Q + q0 + qi2) * NLEV + kq;
-          cp_async8(smem_u32 + TILE_BYTES + ((qi2 * tb.hmax + h) * KC + kk2) * 8, gp);
+          cp_async8(sb + TILE_BYTES + ((qi2 * tb.hmax + h) * KC + kk2) * 8, gp);
         }
       }
     }
@@ -441,9 +444,11 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
 
   double keep[16];  // STAGE3: cf*lap of the first item; TIME_AVG: Qdp(n0)
   issue(0);
+  if (nitems > 1) issue(1);
   for (int j = 0; j < nitems; ++j) {
-    cp_async_wait_all();
-    __syncthreads();  // IN holds item j; every thread is past the copy-out of the previous item
+    if (j + 1 < nitems) cp_async_wait_1(); else cp_async_wait_all();
+    __syncthreads();  // IN[j % NBUF] holds item j; every thread is past the copy-out of the previous item
+    const unsigned char* inb = smem + (j % NBUF) * IN_BYTES;
     const int it = j / NIN, which = j % NIN;
     const int q = it * QI + qi;
     const bool valid = evalid && q < Q;
@@ -452,26 +457,26 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
     double S[16];
     TSE_UNROLL
     for (int c = 0; c < 8; ++c) {
-      const double2 v = lds128(smem, own_base + ((c ^ own_sw) << 4));
+      const double2 v = lds128(inb, own_base + ((c ^ own_sw) << 4));
       S[2 * c] = v.x;
       S[2 * c + 1] = v.y;
     }
     if (a.pending[which]) {  // DSS in the reference's unpack order: S, E, N, W edges, then SW, SE, NE, NW corners
       TSE_UNROLL
-      for (int i = 0; i < 4; ++i) S[i] += lds64(smem, gofs(i));
+      for (int i = 0; i < 4; ++i) S[i] += lds64(inb, gofs(i));
       TSE_UNROLL
-      for (int i = 0; i < 4; ++i) S[3 + 4 * i] += lds64(smem, gofs(4 + i));
+      for (int i = 0; i < 4; ++i) S[3 + 4 * i] += lds64(inb, gofs(4 + i));
       TSE_UNROLL
-      for (int i = 0; i < 4; ++i) S[12 + i] += lds64(smem, gofs(8 + i));
+      for (int i = 0; i < 4; ++i) S[12 + i] += lds64(inb, gofs(8 + i));
       TSE_UNROLL
-      for (int i = 0; i < 4; ++i) S[4 * i] += lds64(smem, gofs(12 + i));
-      S[0] += lds64(smem, gofs(16));
-      S[3] += lds64(smem, gofs(17));
-      S[15] += lds64(smem, gofs(18));
-      S[12] += lds64(smem, gofs(19));
+      for (int i = 0; i < 4; ++i) S[4 * i] += lds64(inb, gofs(12 + i));
+      S[0] += lds64(inb, gofs(16));
+      S[3] += lds64(inb, gofs(17));
+      S[15] += lds64(inb, gofs(18));
+      S[12] += lds64(inb, gofs(19));
     }
-    __syncthreads();  // all reads of IN done: prefetch the next item into it, overlapping the compute below
-    if (j + 1 < nitems) issue(j + 1);
+    __syncthreads();  // all reads of this IN buffer done: refill it with the item after next, overlapping the compute below
+    if (j + NBUF < nitems) issue(j + NBUF);
 
     const bool last_of_iter = (which == NIN - 1);
     if (valid) {
@@ -482,16 +487,16 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
           S[2 * c] *= rd.x;
           S[2 * c + 1] *= rd.y;
         }
-        double mn0 = fmin(S[0], S[1]), mx0 = fmax(S[0], S[1]), mn1 = fmin(S[2], S[3]), mx1 = fmax(S[2], S[3]);
+        double mn0 = dmin(S[0], S[1]), mx0 = dmax(S[0], S[1]), mn1 = dmin(S[2], S[3]), mx1 = dmax(S[2], S[3]);
         TSE_UNROLL
         for (int n = 4; n < 16; n += 4) {
-          mn0 = fmin(mn0, fmin(S[n], S[n + 1]));
-          mx0 = fmax(mx0, fmax(S[n], S[n + 1]));
-          mn1 = fmin(mn1, fmin(S[n + 2], S[n + 3]));
-          mx1 = fmax(mx1, fmax(S[n + 2], S[n + 3]));
+          mn0 = dmin(mn0, dmin(S[n], S[n + 1]));
+          mx0 = dmax(mx0, dmax(S[n], S[n + 1]));
+          mn1 = dmin(mn1, dmin(S[n + 2], S[n + 3]));
+          mx1 = dmax(mx1, dmax(S[n + 2], S[n + 3]));
         }
-        a.qmin_loc[pidx] = fmin(mn0, mn1);
-        a.qmax_loc[pidx] = fmax(mx0, mx1);
+        a.qmin_loc[pidx] = dmin(mn0, mn1);
+        a.qmax_loc[pidx] = dmax(mx0, mx1);
         if (OP == OP_BIHARM_PRE) {
           double lap[16];
           laplace_wk_el(S, D, elb + cfg.T11 * EL_BYTES, elb + cfg.T12 * EL_BYTES, elb + cfg.T22 * EL_BYTES, el, lap);
@@ -538,13 +543,13 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
           for (int c = 0; c < 8; ++c) {
             const double2 rd = lds128(pp + cfg.RDP * PP_BYTES, (c * GPL + pl) * 16);
             const double q0v = S[2 * c] * rd.x, q1v = S[2 * c + 1] * rd.y;
-            mn0 = fmin(mn0, q0v);
-            mx0 = fmax(mx0, q0v);
-            mn1 = fmin(mn1, q1v);
-            mx1 = fmax(mx1, q1v);
+            mn0 = dmin(mn0, q0v);
+            mx0 = dmax(mx0, q0v);
+            mn1 = dmin(mn1, q1v);
+            mx1 = dmax(mx1, q1v);
           }
-          minp = fmin(minp, fmin(mn0, mn1));
-          maxp = fmax(maxp, fmax(mx0, mx1));
+          minp = dmin(minp, dmin(mn0, mn1));
+          maxp = dmax(maxp, dmax(mx0, mx1));
         }
         double y[16];
         asm volatile("" ::: "memory");
@@ -624,12 +629,12 @@ __global__ void __launch_bounds__(256) k_nbr_minmax(Geo G, int Q, const double* 
     const int b = nb[d];
     if (b >= 0) {
       const size_t pb = qplane(b, q, k, Q);
-      mn = fmin(mn, lmin[pb]);
-      mx = fmax(mx, lmax[pb]);
+      mn = dmin(mn, lmin[pb]);
+      mx = dmax(mx, lmax[pb]);
     } else if (b <= -2) {
       const size_t gb = ((size_t)(-b - 2) * 2 * Q + q) * NLEV + k;
-      mn = fmin(mn, ghost_mm[gb]);
-      mx = fmax(mx, ghost_mm[gb + (size_t)Q * NLEV]);
+      mn = dmin(mn, ghost_mm[gb]);
+      mx = dmax(mx, ghost_mm[gb + (size_t)Q * NLEV]);
     }
   }
   qmin[p] = mn;
