@@ -201,7 +201,7 @@ def run_ours(args):
     launches = adv.launch_count - l0
     stage_launches = adv.stage_launch_count - s0
     stage_ms = adv.timer_ms("k_euler_stage")
-    timers = {k: adv.timer_ms(k) for k in ("prim_run", "prim_advance_exp", "prim_advec_tracers_remap_rk2", "euler_step", "vertical_remap")}
+    timers = {k: adv.timer_ms(k) for k in ("prim_run", "prim_advance_exp", "prim_advec_tracers_remap_rk2", "euler_step", "vertical_remap", "bndry_exchange", "edge_pack")}
     if world > 1:
         t = torch.tensor([T_ms, stage_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -99,6 +99,13 @@ struct tse_state {
   int *d_send_src = nullptr, *d_mm_elem = nullptr;
   double *send_q = nullptr, *send_lev = nullptr, *ghost_lev = nullptr, *send_mm = nullptr, *ghost_mm = nullptr;
   long long halo_bytes = 0;  // bytes sent by this rank so far
+  // overlap of the halo exchange with interior compute: groups owning a node that is sent come first, the exchange runs on
+  // comm_stream while the remaining groups are processed
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
+  int *d_glist_b = nullptr, *d_glist_i = nullptr;
+  int n_glist_b = 0, n_glist_i = 0;
+  bool halo_outstanding = false;
   // timers (lazily resolved CUDA events under the reference's GPTL names)
   std::map<std::string, double> timers;
   struct TimerRec { const char* name; cudaEvent_t a, b; };
@@ -220,38 +227,68 @@ int check_device_error(tse_state* s) {
 }
 
 // ---- halo exchange ----------------------------------------------------------------------------
-// one ncclSend + ncclRecv per neighbour rank (a Cycle_t of the reference's schedule), `unit` doubles per ghost slot / bundle
-int exchange(tse_state* s, const double* send, double* recv, size_t unit, bool bundles) {
+// One ncclSend + ncclRecv per neighbour rank (a Cycle_t of the reference's schedule) and per payload, all payloads of one DSS in a
+// single NCCL group (= one fused transfer kernel), like the reference packs all layers of a DSS into one message per neighbour.
+struct Xfer {
+  const double* send;
+  double* recv;
+  size_t unit;   // doubles per ghost slot (or per bundle)
+  bool bundles;  // payload is indexed by (element, direction) bundle instead of by ghost slot
+};
+int exchange(tse_state* s, std::initializer_list<Xfer> xs) {
   if (s->cycles.empty()) return 0;
   if (!s->comm) return fail("halo exchange: this rank has off-GPU neighbours but tse_comm_init was not called");
-  ScopedTimer tm(s, "bndry_exchange");
   NC(ncclGroupStart());
-  for (const auto& c : s->cycles) {
-    const size_t off = (size_t)(bundles ? c.boff : c.off) * unit, cnt = (size_t)(bundles ? c.blen : c.len) * unit;
-    NC(ncclSend(send + off, cnt, ncclDouble, c.peer, s->comm, s->stream));
-    NC(ncclRecv(recv + off, cnt, ncclDouble, c.peer, s->comm, s->stream));
-    s->halo_bytes += (long long)cnt * 8;
-  }
+  for (const auto& c : s->cycles)
+    for (const Xfer& x : xs) {
+      const size_t off = (size_t)(x.bundles ? c.boff : c.off) * x.unit, cnt = (size_t)(x.bundles ? c.blen : c.len) * x.unit;
+      NC(ncclSend(x.send + off, cnt, ncclDouble, c.peer, s->comm, s->comm_stream));
+      NC(ncclRecv(x.recv + off, cnt, ncclDouble, c.peer, s->comm, s->comm_stream));
+      s->halo_bytes += (long long)cnt * 8;
+    }
   NC(ncclGroupEnd());
+  CU(cudaEventRecord(s->ev_halo, s->comm_stream));
+  s->halo_outstanding = true;
   return 0;
 }
-// halo of a pre-DSS tracer buffer -> qghost[buf]
-int exchange_tracer(tse_state* s, int buf) {
-  if (s->cycles.empty()) return 0;
+// the compute stream must not read ghosts before the exchange has landed
+int wait_halo(tse_state* s) {
+  if (!s->halo_outstanding) return 0;
+  ScopedTimer tm(s, "bndry_exchange");  // time the compute stream is stalled on the halo (what is not hidden by interior compute)
+  CU(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+  s->halo_outstanding = false;
+  return 0;
+}
+// the comm stream starts packing once the boundary groups of the producing kernel are done
+int comm_after_boundary(tse_state* s) {
+  CU(cudaEventRecord(s->ev_boundary, s->stream));
+  CU(cudaStreamWaitEvent(s->comm_stream, s->ev_boundary, 0));
+  return 0;
+}
+int pack_tracer(tse_state* s, int buf) {
   const size_t total = (size_t)s->nghost * s->Q * NLEV;
-  k_pack_tracer<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(s->qbuf[buf], s->d_send_src, s->nghost, s->Q, s->send_q);
+  k_pack_tracer<<<(unsigned)((total + 255) / 256), 256, 0, s->comm_stream>>>(s->qbuf[buf], s->d_send_src, s->nghost, s->Q, s->send_q);
   ++s->launches;
   CU(cudaGetLastError());
-  return exchange(s, s->send_q, s->qghost[buf], (size_t)s->Q * NLEV, false);
+  return 0;
 }
-int exchange_minmax(tse_state* s) {
-  if (s->cycles.empty()) return 0;
+int pack_minmax(tse_state* s) {
   const size_t total = (size_t)s->nbundle * s->Q * NLEV;
-  k_pack_minmax<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(s->qmin_loc, s->qmax_loc, s->d_mm_elem, s->nbundle, s->Q, s->send_mm);
+  k_pack_minmax<<<(unsigned)((total + 255) / 256), 256, 0, s->comm_stream>>>(s->qmin_loc, s->qmax_loc, s->d_mm_elem, s->nbundle, s->Q, s->send_mm);
   ++s->launches;
   CU(cudaGetLastError());
-  return exchange(s, s->send_mm, s->ghost_mm, (size_t)2 * s->Q * NLEV, true);
+  return 0;
 }
+int pack_level(tse_state* s, const double* f) {
+  const size_t total = (size_t)s->nghost * NLEV;
+  k_pack_level<<<(unsigned)((total + 255) / 256), 256, 0, s->comm_stream>>>(f, s->geo.spheremp, s->d_send_src, s->nghost, s->send_lev);
+  ++s->launches;
+  CU(cudaGetLastError());
+  return 0;
+}
+Xfer xfer_tracer(tse_state* s, int buf) { return Xfer{s->send_q, s->qghost[buf], (size_t)s->Q * NLEV, false}; }
+Xfer xfer_minmax(tse_state* s) { return Xfer{s->send_mm, s->ghost_mm, (size_t)2 * s->Q * NLEV, true}; }
+Xfer xfer_level(tse_state* s) { return Xfer{s->send_lev, s->ghost_lev, (size_t)NLEV, false}; }
 
 TileArgs tile_args(const tse_state* s) {
   TileArgs a{};
@@ -268,13 +305,33 @@ void set_src(const tse_state* s, TileArgs& a, int i, int buf, int pending) {
   a.pending[i] = pending;
 }
 template <int OP>
-void launch_tile(tse_state* s, const TileArgs& a) {
-  k_tile<OP><<<s->ngroups * NKC, TT, tile_smem_bytes(OP, s->tiles.hmax), s->stream>>>(s->geo, s->dvv, s->tiles, a);
+void launch_tile(tse_state* s, TileArgs a, const int* glist = nullptr, int ngl = 0) {
+  a.glist = glist;
+  const int ng = glist ? ngl : s->ngroups;
+  if (ng == 0) return;
+  k_tile<OP><<<ng * NKC, TT, tile_smem_bytes(OP, s->tiles.hmax), s->stream>>>(s->geo, s->dvv, s->tiles, a);
   ++s->launches;
 }
-// neighbor_minmax (viscosity_mod.F90:748-816): exchange of the element extrema + 9-way min/max
+// producer launch of a field whose boundary nodes are exchanged: boundary groups, then (after `start_comm` queued the pack and
+// the exchange on the comm stream) the interior groups
+template <int OP, class F>
+int launch_tile_overlapped(tse_state* s, const TileArgs& a, F start_comm) {
+  if (s->cycles.empty()) {
+    launch_tile<OP>(s, a);
+    CU(cudaGetLastError());
+    return 0;
+  }
+  launch_tile<OP>(s, a, s->d_glist_b, s->n_glist_b);
+  CU(cudaGetLastError());
+  if (comm_after_boundary(s)) return 1;
+  if (start_comm()) return 1;
+  launch_tile<OP>(s, a, s->d_glist_i, s->n_glist_i);
+  CU(cudaGetLastError());
+  return 0;
+}
+// neighbor_minmax (viscosity_mod.F90:748-816) after the element extrema of off-GPU neighbours have arrived: 9-way min/max
 int neighbor_minmax(tse_state* s) {
-  if (exchange_minmax(s)) return 1;
+  if (wait_halo(s)) return 1;
   const size_t total = (size_t)s->ngroups * NKC * s->Q * GPL;
   k_nbr_minmax<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(s->geo, s->Q, s->qmin_loc, s->qmax_loc, s->ghost_mm, s->qmin, s->qmax);
   ++s->launches;
@@ -284,6 +341,7 @@ int neighbor_minmax(tse_state* s) {
 
 int resolve_slot(tse_state* s, int tl) {
   if (!s->slot_pending[tl]) return 0;
+  if (wait_halo(s)) return 1;
   const int other = s->slot_buf[3 - tl], in = s->slot_buf[tl];
   const int out = pick_buffer({in, other});
   TileArgs a = tile_args(s);
@@ -297,16 +355,14 @@ int resolve_slot(tse_state* s, int tl) {
 }
 
 // DSS of the extra level field of euler_step (prim_advection_mod.F90:913-919, 943-958)
-int dss_level_field(tse_state* s, int DSSopt) {
+double** level_field(tse_state* s, int DSSopt) {
+  return DSSopt == TSE_DSS_ETA ? &s->eta_dot : DSSopt == TSE_DSS_OMEGA ? &s->omega_p : DSSopt == TSE_DSS_DIV_VDP_AVE ? &s->divdp_proj : nullptr;
+}
+int dss_level_field(tse_state* s, int DSSopt) {  // the halo of the field (ghost_lev) must already have been exchanged
   double** f = DSSopt == TSE_DSS_ETA ? &s->eta_dot : DSSopt == TSE_DSS_OMEGA ? &s->omega_p : DSSopt == TSE_DSS_DIV_VDP_AVE ? &s->divdp_proj : nullptr;
   if (DSSopt != TSE_DSS_NO_VAR && !f) return fail("tse_euler_step: DSSopt=%d", DSSopt);
   if (!f) return 0;
-  if (!s->cycles.empty()) {
-    const size_t total = (size_t)s->nghost * NLEV;
-    k_pack_level<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(*f, s->geo.spheremp, s->d_send_src, s->nghost, s->send_lev);
-    ++s->launches;
-    if (exchange(s, s->send_lev, s->ghost_lev, NLEV, false)) return 1;
-  }
+  if (wait_halo(s)) return 1;
   k_dss_level<<<level_blocks(s), 128, 0, s->stream>>>(s->geo, *f, s->ghost_lev, s->lev_tmp);
   ++s->launches;
   CU(cudaGetLastError());
@@ -465,6 +521,19 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
       nbr8[(size_t)e * 8 + 4 + x] = gm < 0 ? -1 : nbr_of(gm);
     }
   }
+  if (nghost > 0) {
+    std::vector<char> is_b(s->ngroups, 0);
+    for (int i = 0; i < nghost; ++i) is_b[(send_src[i] >> 4) / GE] = 1;
+    for (int b = 0; b < s->nbundle; ++b) is_b[mm_elem[b] / GE] = 1;
+    std::vector<int> gb, gi;
+    for (int g = 0; g < s->ngroups; ++g) (is_b[g] ? gb : gi).push_back(g);
+    s->n_glist_b = (int)gb.size();
+    s->n_glist_i = (int)gi.size();
+    if (upload(s, &s->d_glist_b, gb) || upload(s, &s->d_glist_i, gi)) return 1;
+    CU(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&s->ev_boundary, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming));
+  }
   int *d_gsrc, *d_nbr8;
   if (upload(s, &d_gsrc, gsrc) || upload(s, &d_nbr8, nbr8) || upload(s, &s->d_send_src, send_src) || upload(s, &s->d_mm_elem, mm_elem))
     return 1;
@@ -581,7 +650,11 @@ int tse_finalize(tse_handle s) {
   if (!s) return 0;
   cudaStreamSynchronize(s->stream);
   resolve_timers(s);
+  if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
   if (s->comm) ncclCommDestroy(s->comm);
+  if (s->ev_boundary) cudaEventDestroy(s->ev_boundary);
+  if (s->ev_halo) cudaEventDestroy(s->ev_halo);
+  if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
   for (cudaEvent_t e : s->event_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : s->marks)
     if (e) cudaEventDestroy(e);
@@ -592,6 +665,7 @@ int tse_finalize(tse_handle s) {
 }
 
 int tse_synchronize(tse_handle s) {
+  if (s->comm_stream) CU(cudaStreamSynchronize(s->comm_stream));
   CU(cudaStreamSynchronize(s->stream));
   return check_device_error(s);
 }
@@ -738,48 +812,58 @@ int tse_euler_step(tse_handle s, int np1_qdp, int n0_qdp, double dt, int DSSopt,
   a.dt = dt;
   a.visc_coef = -3.0 * dt * s->cfg.nu_q;  // rhs_viss = 3 (prim_advection_mod.F90:797,823)
   int tmp = -1;
+  if (wait_halo(s)) return 1;
   if (rhs_multiplier == 0) {
     // qmin/qmax = element extrema of Q = Qdp/dp, then min/max over the 8 neighbours (:764-778)
     set_src(s, a, 0, in, in_pending);
-    launch_tile<OP_MINMAX>(s, a);
+    if (launch_tile_overlapped<OP_MINMAX>(s, a, [&]() { return pack_minmax(s) || exchange(s, {xfer_minmax(s)}); })) return 1;
     if (neighbor_minmax(s)) return 1;
   } else if (rhs_multiplier == 2) {
-    // biharmonic_wk_scalar_minmax (viscosity_mod.F90:353-442): lap(Q), one exchange carrying lap + extrema, second lap in the stage kernel
+    // biharmonic_wk_scalar_minmax (viscosity_mod.F90:353-442): lap(Q); one message per neighbour carries lap(Q) and the extrema
+    // (3*nlev*qsize layers in the reference); the second laplacian runs inside the stage kernel
     tmp = pick_buffer({in, other});
     if (tmp < 0) return fail("tse_euler_step: no free tracer buffer");
     set_src(s, a, 0, in, in_pending);
     a.out = s->qbuf[tmp];
-    launch_tile<OP_BIHARM_PRE>(s, a);
-    CU(cudaGetLastError());
-    if (exchange_tracer(s, tmp)) return 1;
+    if (launch_tile_overlapped<OP_BIHARM_PRE>(
+            s, a, [&]() { return pack_tracer(s, tmp) || pack_minmax(s) || exchange(s, {xfer_tracer(s, tmp), xfer_minmax(s)}); }))
+      return 1;
     if (neighbor_minmax(s)) return 1;
   }
   const int outb = pick_buffer({in, other, tmp});
   if (outb < 0) return fail("tse_euler_step: no free tracer buffer");
   a.out = s->qbuf[outb];
+  double** lf = level_field(s, DSSopt);
+  if (DSSopt != TSE_DSS_NO_VAR && !lf) return fail("tse_euler_step: DSSopt=%d", DSSopt);
+  // the bndry_exchangeV of the stage (:923-927): Qdp(np1) and the extra level field travel in one message per neighbour while the
+  // interior groups are still being computed; the unpack of Qdp happens in the next reader
+  auto stage_comm = [&]() -> int {
+    if (pack_tracer(s, outb)) return 1;
+    if (lf) return pack_level(s, *lf) || exchange(s, {xfer_tracer(s, outb), xfer_level(s)});
+    return exchange(s, {xfer_tracer(s, outb)});
+  };
   {
     ScopedTimer tk(s, "k_euler_stage");
     if (rhs_multiplier == 2) {
       set_src(s, a, 0, tmp, 1);
       set_src(s, a, 1, in, in_pending);
-      launch_tile<OP_STAGE3>(s, a);
+      if (launch_tile_overlapped<OP_STAGE3>(s, a, stage_comm)) return 1;
     } else {
       set_src(s, a, 0, in, in_pending);
-      if (rhs_multiplier == 0) launch_tile<OP_STAGE1>(s, a);
-      else launch_tile<OP_STAGE2>(s, a);
+      if (rhs_multiplier == 0) {
+        if (launch_tile_overlapped<OP_STAGE1>(s, a, stage_comm)) return 1;
+      } else if (launch_tile_overlapped<OP_STAGE2>(s, a, stage_comm)) return 1;
     }
     ++s->stage_launches;
   }
-  CU(cudaGetLastError());
   s->slot_buf[np1_qdp] = outb;
   s->slot_pending[np1_qdp] = 1;
-  if (exchange_tracer(s, outb)) return 1;  // the bndry_exchangeV of the stage (:923-927); the unpack happens in the next reader
   return dss_level_field(s, DSSopt);
 }
 
 int tse_qdp_time_avg(tse_handle s, int rkstage, int n0_qdp, int np1_qdp) {
   if (check_tl(np1_qdp) || check_tl(n0_qdp) || n0_qdp == np1_qdp) return fail("tse_qdp_time_avg: bad time levels %d %d", n0_qdp, np1_qdp);
-  if (resolve_slot(s, n0_qdp)) return 1;
+  if (resolve_slot(s, n0_qdp) || wait_halo(s)) return 1;
   const int in = s->slot_buf[np1_qdp], q0 = s->slot_buf[n0_qdp];
   const int outb = pick_buffer({in, q0});
   TileArgs a = tile_args(s);
@@ -875,7 +959,7 @@ int tse_prim_run_subcycle(tse_handle s, double tstep, int* nstep_io) {
 // global tracer mass sum_e sum_k sum_ij spheremp*Qdp with an order-independent fixed-point sum
 // (the repro_sum idea, repro_sum_mod.F90:216-628: bitwise identical for any element order / GPU count)
 int tse_diag_mass(tse_handle s, int tl, double* mass) {
-  if (check_tl(tl)) return 1;
+  if (check_tl(tl) || wait_halo(s)) return 1;
   const DssView v = view(s, s->slot_buf[tl], s->slot_pending[tl]);
   const int Q = s->Q;
   CU(cudaMemsetAsync(s->d_maxbits, 0, sizeof(unsigned long long) * Q, s->stream));

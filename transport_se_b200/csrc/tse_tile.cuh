@@ -58,6 +58,7 @@ struct TileArgs {
   const double* dp0;
   double *qmin, *qmax, *qmin_loc, *qmax_loc;
   int Q;
+  const int* glist;  // optional list of groups this launch covers (boundary groups first, interior groups while the halo is in flight)
 };
 
 constexpr int PP_BYTES = GPL * 128;  // per-plane package field (8 KB)
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
   const int ZERO_OFF = TILE_BYTES + QI * tb.hmax * KC * 8;
 
   const int t = threadIdx.x;
-  const int g = blockIdx.x / NKC, kc = blockIdx.x % NKC;
+  const int g = a.glist ? a.glist[blockIdx.x / NKC] : blockIdx.x / NKC, kc = blockIdx.x % NKC;
   // warp = 2 elements x 4 levels x 4 tracers
   const int w = t >> 5, lane = t & 31;
   const int kk = lane & 3, el = EPW * w + ((lane >> 2) % EPW), qi = lane / (4 * EPW);
