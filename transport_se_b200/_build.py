@@ -33,9 +33,9 @@ def cuda_sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def build_cuda(force=False, verbose=False):
+def build_cuda(force=False, verbose=False, out=None):
     """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -> libtse_cuda.so (cross-compiles without a GPU)."""
-    out = os.path.join(_HERE, "libtse_cuda.so")
+    out = out or os.path.join(_HERE, "libtse_cuda.so")
     srcs = cuda_sources()
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp", ".h"))]
     deps.append(os.path.join(ROOT, "include", "tse.h"))

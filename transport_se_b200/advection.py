@@ -54,7 +54,7 @@ def cuda_lib():
     """Load libtse_cuda.so (built in-tree by transport_se_b200._build.build_cuda / __graft_entry__.build)."""
     global _LIB
     if _LIB is None:
-        path = os.path.join(_HERE, "libtse_cuda.so")
+        path = os.environ.get("TSE_CUDA_LIB") or os.path.join(_HERE, "libtse_cuda.so")  # override: kernel-variant experiments (tools/)
         if not os.path.exists(path):
             raise RuntimeError("libtse_cuda.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback)")
         L = C.CDLL(path)

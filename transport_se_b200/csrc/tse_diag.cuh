@@ -17,17 +17,20 @@ __device__ __forceinline__ double plane_mass(const Geo& G, const DssView& in, co
   return J;
 }
 
+// a warp holds 32 / SEG tracers of SEG planes each (SEG = 32 when a tracer's GPL planes fill whole warps)
+constexpr int SEG = GPL < 32 ? GPL : 32;
+
 __global__ void __launch_bounds__(GPL* QPB) k_mass_max(Geo G, DssView in, unsigned long long* __restrict__ maxbits) {
   const ThreadPlane t = thread_plane(G, in.Q);
   unsigned long long b = 0;
   if (t.valid) b = (unsigned long long)__double_as_longlong(fabs(plane_mass(G, in, t)));
   TSE_UNROLL
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = SEG / 2; o > 0; o >>= 1) {
     const unsigned long long x = __shfl_xor_sync(0xffffffffu, b, o);
     b = x > b ? x : b;
   }
-  const int q = blockIdx.y * QPB + threadIdx.x / GPL;  // uniform per warp
-  if ((threadIdx.x & 31) == 0 && q < in.Q) atomicMax(maxbits + q, b);
+  const int q = blockIdx.y * QPB + threadIdx.x / GPL;  // uniform per SEG lanes
+  if ((threadIdx.x & (SEG - 1)) == 0 && q < in.Q) atomicMax(maxbits + q, b);
 }
 
 __global__ void __launch_bounds__(GPL* QPB) k_mass_fixed(Geo G, DssView in, const int* __restrict__ shift, long long* __restrict__ acc) {
@@ -41,11 +44,11 @@ __global__ void __launch_bounds__(GPL* QPB) k_mass_fixed(Geo G, DssView in, cons
     lo = (long long)trunc(scalbn(x - xi, 40));
   }
   TSE_UNROLL
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = SEG / 2; o > 0; o >>= 1) {
     hi += __shfl_xor_sync(0xffffffffu, hi, o);
     lo += __shfl_xor_sync(0xffffffffu, lo, o);
   }
-  if ((threadIdx.x & 31) == 0 && q < in.Q) {
+  if ((threadIdx.x & (SEG - 1)) == 0 && q < in.Q) {
     atomicAdd(reinterpret_cast<unsigned long long*>(acc + 2 * q), (unsigned long long)hi);
     atomicAdd(reinterpret_cast<unsigned long long*>(acc + 2 * q + 1), (unsigned long long)lo);
   }

@@ -4,11 +4,11 @@
 // Qdp(np,np,nlev,qsize_d,2) per element.  On the device the private copy is tiled
 // for the access pattern of the stage kernels:
 //
-//   tracer field  Q[g][kc][q][el][kk][16]      g  = group of GE=16 consecutive elements (internal order)
+//   tracer field  Q[g][kc][q][el][kk][16]      g  = group of GE consecutive elements (internal order)
 //   level field   F[g][kc][el][kk][16]         kc = chunk of KC=4 levels, kk = level in chunk
 //   vn0           V[g][kc][c][el][kk][16]      el = element in group, 16 = (i,j) nodes, i fastest
 //
-// so that the 16 x KC planes one CTA needs for a tracer are one contiguous 8 KB block
+// so that the GE x KC planes one CTA needs for a tracer are one contiguous 8 KB block
 // and consecutive tracers of the same (group, level chunk) follow each other.
 // Internal element order follows the space-filling curve, so a group is a compact
 // patch and most DSS neighbours of an element sit in the same group.
@@ -23,7 +23,10 @@ constexpr int NPSQ = 16;
 constexpr int NLEV = 72;
 constexpr int KC = 4;            // levels per chunk
 constexpr int NKC = NLEV / KC;   // 18
-constexpr int GE = 16;           // elements per group
+#ifndef TSE_GE
+#define TSE_GE 16
+#endif
+constexpr int GE = TSE_GE;       // elements per group (16 = a 4x4 patch at ne = 2^k; 4 measured slower: 2x the halo, 4x the CTA prologues)
 constexpr int GPL = GE * KC;     // planes per (group, chunk, tracer) = 64
 
 // direction order of control_mod.F90:173-181 (0-based)

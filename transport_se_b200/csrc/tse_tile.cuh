@@ -37,7 +37,14 @@ constexpr int QI = TSE_QI;             // tracers per pipeline step
 constexpr int TT = QI * GPL;           // threads per CTA (256 for QI = 4)
 constexpr int TILE_BYTES = TT * 128;   // 32 KB for QI = 4
 constexpr int HPRE = 512 / TT;         // halo entries per thread resolved before the tracer loop (covers hmax <= 128)
-constexpr int EPW = 8 / QI;            // elements per warp
+constexpr int QW = QI < 8 ? QI : 8;    // tracers per warp
+constexpr int EPW = 8 / QW;            // elements per warp (1 for QI >= 8: the limiter's work is a property of the element)
+static_assert(KC == 4 && (QI % QW) == 0 && (GE % EPW) == 0 && TT % 32 == 0 && TT <= 512, "warp mapping");
+static_assert(EPW > 1 || (TT / 8) % GPL == 0 || GPL % (TT / 8) == 0, "swizzle");
+
+// XOR swizzle of the 16-byte units of a 128-byte plane: distinct over the 8 planes a quarter-warp reads together
+// (lanes 0..7 = 4 levels x 2 elements for EPW > 1, 4 levels x 2 tracers for EPW == 1)
+__host__ __device__ constexpr int swz(int p) { return EPW > 1 ? (p & 7) : ((p & 3) | (((p / GPL) & 1) << 2)); }
 
 enum TileOp { OP_MINMAX = 0, OP_STAGE1, OP_STAGE2, OP_STAGE3, OP_BIHARM_PRE, OP_TIME_AVG, OP_RESOLVE };
 
@@ -67,16 +74,16 @@ constexpr int EL_BYTES = GE * 128;   // per-element package field (2 KB)
 // which package fields an op keeps in shared memory
 struct TileCfg {
   int npp, nel, has_out;
-  int U1, U2, CL, RDP;            // per-plane field slots
+  int U1, U2, CL, RDP, RC;        // per-plane field slots
   int E1, E2, RSPH, T11, T12, T22;  // per-element field slots
 };
 __host__ __device__ constexpr TileCfg tile_cfg(int op) {
-  return op == OP_STAGE1 ? TileCfg{3, 2, 1, 0, 1, 2, -1, 0, 1, -1, -1, -1, -1}
-       : op == OP_STAGE2 ? TileCfg{4, 2, 1, 0, 1, 2, 3, 0, 1, -1, -1, -1, -1}
-       : op == OP_STAGE3 ? TileCfg{3, 6, 1, 0, 1, 2, -1, 0, 1, 2, 3, 4, 5}
-       : op == OP_MINMAX ? TileCfg{1, 0, 0, -1, -1, -1, 0, -1, -1, -1, -1, -1, -1}
-       : op == OP_BIHARM_PRE ? TileCfg{1, 3, 1, -1, -1, -1, 0, -1, -1, -1, 0, 1, 2}
-                             : TileCfg{0, 1, 1, -1, -1, -1, -1, -1, -1, 0, -1, -1, -1};
+  return op == OP_STAGE1 ? TileCfg{4, 2, 1, 0, 1, 2, -1, 3, 0, 1, -1, -1, -1, -1}
+       : op == OP_STAGE2 ? TileCfg{5, 2, 1, 0, 1, 2, 3, 4, 0, 1, -1, -1, -1, -1}
+       : op == OP_STAGE3 ? TileCfg{4, 6, 1, 0, 1, 2, -1, 3, 0, 1, 2, 3, 4, 5}
+       : op == OP_MINMAX ? TileCfg{1, 0, 0, -1, -1, -1, 0, -1, -1, -1, -1, -1, -1, -1}
+       : op == OP_BIHARM_PRE ? TileCfg{1, 3, 1, -1, -1, -1, 0, -1, -1, -1, -1, 0, 1, 2}
+                             : TileCfg{0, 1, 1, -1, -1, -1, -1, -1, -1, -1, 0, -1, -1, -1};
 }
 __host__ __device__ constexpr int tile_in_bytes(int hmax) { return TILE_BYTES + QI * hmax * KC * 8 + 16; }
 constexpr int NBUF = 2;  // IN buffers: two tiles are in flight while a third is being processed from registers
@@ -104,11 +111,18 @@ __device__ __forceinline__ double2 lds128v(unsigned addr) {
   return v;
 }
 
-// limiter_optim_iter_full (prim_advection_mod.F90:976-1094) on y = c*x (mass contributions) instead of x:
-// x > maxp  <=>  y > maxp*c ; addmass += (x-maxp)*c = y - maxp*c ; x += inc  <=>  y += inc*c ; result ptens*sphweights = y.
-// c is read from the per-plane package in shared memory (cbase = shared address of chunk 0 of this plane, chunk stride
-// GPL*16 bytes).  Sums use 4 interleaved partial accumulators (fixed order, identical on every GPU count).
-__device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, double sumc, double& minp, double& maxp) {
+// limiter_optim_iter_full (prim_advection_mod.F90:976-1094).  On entry y = c*x (mass contributions, c = sphweights*dpmass);
+// c and rc = 1/c are read from the per-plane package in shared memory (cbase/rcbase = shared address of chunk 0 of this
+// plane, chunk stride GPL*16 bytes).  Sums use 4 interleaved partial accumulators (fixed order, identical on every GPU count).
+//
+// Fast path: mass = sum(y) and the min/max relaxation (:1016-1029) need no x; if no x = y*rc lies outside [minp, maxp] the
+// reference's first sweep finds addmass = 0 and leaves (:1047), so y is returned untouched.
+// Slow path (x in place of y): sweep 1 clips against both bounds.  From then on the direction is fixed: redistributing
+// addmass > 0 raises nodes below maxp, so later sweeps can only find nodes above maxp and addmass stays >= 0 (and the mirror
+// image for addmass < 0); the lower-bound test of the reference's sweeps 2..15 is then never taken.  Working on z = -x,
+// bound -minp for the downward case (negation is exact) leaves one code path, whose sweep fuses "add the increment"
+// (:1052-1078 of sweep i), "clip" (:1037-1045 of sweep i+1) and the next weightssum.
+__device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsigned rcbase, double sumc, double& minp, double& maxp) {
   const double tol_limiter = (double)5e-14f;
   if (sumc <= 0.0) return;
   double mass;
@@ -125,50 +139,103 @@ __device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, doubl
   }
   if (mass < minp * sumc) minp = mass / sumc;
   if (mass > maxp * sumc) maxp = mass / sumc;
+  bool viol = false;
+  TSE_UNROLL
+  for (int cc = 0; cc < 8; ++cc) {
+    const double2 r = lds128v(rcbase + cc * GPL * 16);
+    const double x0 = y[2 * cc] * r.x, x1 = y[2 * cc + 1] * r.y;
+    viol |= (x0 > maxp) | (x0 < minp) | (x1 > maxp) | (x1 < minp);
+  }
+  if (!viol) return;
+
   const double thresh = tol_limiter * fabs(mass);
-#pragma unroll 1
-  for (int iter = 1; iter <= NPSQ - 1; ++iter) {
+  TSE_UNROLL
+  for (int cc = 0; cc < 8; ++cc) {
+    const double2 r = lds128v(rcbase + cc * GPL * 16);
+    y[2 * cc] *= r.x;
+    y[2 * cc + 1] *= r.y;
+  }
+  double am;
+  {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     TSE_UNROLL
     for (int cc = 0; cc < 8; cc += 2) {
       const double2 ca = lds128v(cbase + cc * GPL * 16), cb = lds128v(cbase + (cc + 1) * GPL * 16);
-      const double cv[4] = {ca.x, ca.y, cb.x, cb.y};
+      const int n = 2 * cc;
+      double t;
+      t = dmin(dmax(y[n], minp), maxp);         a0 = fma(y[n] - t, ca.x, a0);     y[n] = t;
+      t = dmin(dmax(y[n + 1], minp), maxp);     a1 = fma(y[n + 1] - t, ca.y, a1); y[n + 1] = t;
+      t = dmin(dmax(y[n + 2], minp), maxp);     a2 = fma(y[n + 2] - t, cb.x, a2); y[n + 2] = t;
+      t = dmin(dmax(y[n + 3], minp), maxp);     a3 = fma(y[n + 3] - t, cb.y, a3); y[n + 3] = t;
+    }
+    am = (a0 + a1) + (a2 + a3);
+  }
+  if (fabs(am) > thresh) {
+    const bool up = am > 0.0;
+    const double bz = up ? maxp : -minp;
+    if (!up) {
+      am = -am;
       TSE_UNROLL
-      for (int u = 0; u < 4; ++u) {
-        const int n = 2 * cc + u;
-        const double hi = maxp * cv[u], lo = minp * cv[u];
-        const double tcl = dmin(dmax(y[n], lo), hi);
-        const double d = y[n] - tcl;  // (x-maxp)*c above, -(minp-x)*c below, 0 inside
-        y[n] = tcl;
-        if (u == 0) a0 += d;
-        if (u == 1) a1 += d;
-        if (u == 2) a2 += d;
-        if (u == 3) a3 += d;
+      for (int n = 0; n < 16; ++n) y[n] = -y[n];
+    }
+    double wsum;
+    {
+      double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+      TSE_UNROLL
+      for (int cc = 0; cc < 8; cc += 2) {
+        const double2 ca = lds128v(cbase + cc * GPL * 16), cb = lds128v(cbase + (cc + 1) * GPL * 16);
+        const int n = 2 * cc;
+        if (y[n] < bz) w0 += ca.x;
+        if (y[n + 1] < bz) w1 += ca.y;
+        if (y[n + 2] < bz) w2 += cb.x;
+        if (y[n + 3] < bz) w3 += cb.y;
       }
+      wsum = (w0 + w1) + (w2 + w3);
     }
-    const double addmass = (a0 + a1) + (a2 + a3);
-    if (fabs(addmass) <= thresh) break;
-    // nodes not at the bound the mass is pushed toward share addmass (same increment of x for all of them)
-    const bool up = addmass > 0.0;
-    const double bnd = up ? maxp : minp;
-    double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
-    TSE_UNROLL
-    for (int cc = 0; cc < 8; cc += 2) {
-      const double2 ca = lds128v(cbase + cc * GPL * 16), cb = lds128v(cbase + (cc + 1) * GPL * 16);
-      const int n = 2 * cc;
-      if (up ? (y[n] < bnd * ca.x) : (y[n] > bnd * ca.x)) w0 += ca.x;
-      if (up ? (y[n + 1] < bnd * ca.y) : (y[n + 1] > bnd * ca.y)) w1 += ca.y;
-      if (up ? (y[n + 2] < bnd * cb.x) : (y[n + 2] > bnd * cb.x)) w2 += cb.x;
-      if (up ? (y[n + 3] < bnd * cb.y) : (y[n + 3] > bnd * cb.y)) w3 += cb.y;
+#pragma unroll 1
+    for (int iter = 1; iter <= NPSQ - 1; ++iter) {
+      const double inc = am / wsum;
+      if (iter == NPSQ - 1) {  // the reference's last sweep redistributes without a further clip
+        TSE_UNROLL
+        for (int n = 0; n < 16; ++n)
+          if (y[n] < bz) y[n] += inc;
+        break;
+      }
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+      TSE_UNROLL
+      for (int cc = 0; cc < 8; cc += 2) {
+        const double2 ca = lds128v(cbase + cc * GPL * 16), cb = lds128v(cbase + (cc + 1) * GPL * 16);
+        const double cv[4] = {ca.x, ca.y, cb.x, cb.y};
+        TSE_UNROLL
+        for (int u = 0; u < 4; ++u) {
+          const int n = 2 * cc + u;
+          double z = y[n];
+          if (z < bz) z += inc;
+          const double d = z - bz;
+          double ad = 0.0, wd = 0.0;
+          if (d > 0.0) { ad = d; z = bz; }
+          if (d < 0.0) wd = cv[u];
+          y[n] = z;
+          if (u == 0) { a0 = fma(ad, cv[u], a0); w0 += wd; }
+          if (u == 1) { a1 = fma(ad, cv[u], a1); w1 += wd; }
+          if (u == 2) { a2 = fma(ad, cv[u], a2); w2 += wd; }
+          if (u == 3) { a3 = fma(ad, cv[u], a3); w3 += wd; }
+        }
+      }
+      am = (a0 + a1) + (a2 + a3);
+      wsum = (w0 + w1) + (w2 + w3);
+      if (am <= thresh) break;
     }
-    const double inc = addmass / ((w0 + w1) + (w2 + w3));
-    TSE_UNROLL
-    for (int cc = 0; cc < 8; ++cc) {
-      const double2 ca = lds128v(cbase + cc * GPL * 16);
-      const int n = 2 * cc;
-      if (up ? (y[n] < bnd * ca.x) : (y[n] > bnd * ca.x)) y[n] = fma(inc, ca.x, y[n]);
-      if (up ? (y[n + 1] < bnd * ca.y) : (y[n + 1] > bnd * ca.y)) y[n + 1] = fma(inc, ca.y, y[n + 1]);
+    if (!up) {
+      TSE_UNROLL
+      for (int n = 0; n < 16; ++n) y[n] = -y[n];
     }
+  }
+  TSE_UNROLL
+  for (int cc = 0; cc < 8; ++cc) {
+    const double2 c = lds128v(cbase + cc * GPL * 16);
+    y[2 * cc] *= c.x;
+    y[2 * cc + 1] *= c.y;
   }
 }
 
@@ -258,9 +325,9 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
 
   const int t = threadIdx.x;
   const int g = a.glist ? a.glist[blockIdx.x / NKC] : blockIdx.x / NKC, kc = blockIdx.x % NKC;
-  // warp = 2 elements x 4 levels x 4 tracers
+  // warp = EPW elements x 4 levels x QW tracers
   const int w = t >> 5, lane = t & 31;
-  const int kk = lane & 3, el = EPW * w + ((lane >> 2) % EPW), qi = lane / (4 * EPW);
+  const int kk = lane & 3, el = EPW * (w % (GE / EPW)) + ((lane >> 2) % EPW), qi = QW * (w / (GE / EPW)) + (lane >> 2) / EPW;
   const int pl = el * KC + kk;   // plane within one tracer's tile
   const int p = qi * GPL + pl;   // plane within the QI-tracer tile
   const int e = g * GE + el, k = kc * KC + kk;
@@ -308,7 +375,7 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
     TSE_UNROLL
     for (int cc = 0; cc < 8 / PARTS; ++cc) {
       const int c = part * (8 / PARTS) + cc, n = 2 * c;
-      double2 u1 = make_double2(0, 0), u2 = u1, cl = make_double2(1, 1), rd = make_double2(1, 1);
+      double2 u1 = make_double2(0, 0), u2 = u1, cl = make_double2(1, 1), rd = make_double2(1, 1), rcl = make_double2(1, 1);
       if (pe < G.nelem) {
         const size_t lp = lplane(pe, pk) * 16 + n, gb = (size_t)pe * 16 + n;
         const double2 dpv = *reinterpret_cast<const double2*>(a.dp + lp);
@@ -330,6 +397,7 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
           u1 = make_double2((m11.x * vs10 + m12.x * vs20) * rx0, (m11.y * vs11 + m12.y * vs21) * rx1);
           u2 = make_double2((m21.x * vs10 + m22.x * vs20) * rx0, (m21.y * vs11 + m22.y * vs21) * rx1);
           cl = make_double2(sp.x * (dps0 - a.dt * dd.x), sp.y * (dps1 - a.dt * dd.y));
+          rcl = make_double2(1.0 / cl.x, 1.0 / cl.y);
         }
       }
       const int off = (c * GPL + ppl) * 16;
@@ -337,6 +405,7 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
       if (cfg.U2 >= 0) *reinterpret_cast<double2*>(pp + cfg.U2 * PP_BYTES + off) = u2;
       if (cfg.CL >= 0) *reinterpret_cast<double2*>(pp + cfg.CL * PP_BYTES + off) = cl;
       if (cfg.RDP >= 0) *reinterpret_cast<double2*>(pp + cfg.RDP * PP_BYTES + off) = rd;
+      if (cfg.RC >= 0) *reinterpret_cast<double2*>(pp + cfg.RC * PP_BYTES + off) = rcl;
     }
   }
 
@@ -351,7 +420,7 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
       if (code >= 256) off = TILE_BYTES + ((qi * tb.hmax + (code - 256)) * KC + kk) * 8;
       else if (code >= 0) {
         const int p2 = qi * GPL + (code >> 4) * KC + kk, node = code & 15;
-        off = p2 * 128 + ((((node >> 1) ^ (p2 & 7))) << 4) + (node & 1) * 8;
+        off = p2 * 128 + ((((node >> 1) ^ swz(p2))) << 4) + (node & 1) * 8;
       }
       // IN buffer is < 512 KB / 8: store offsets in units of 8 bytes
       if (s & 1) goff[s >> 1] |= (unsigned)(off >> 3) << 16;
@@ -384,8 +453,12 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
   const int nitems = nit * NIN;
   const size_t cta_base = ((size_t)g * NKC + kc) * Q * GPL * 16;  // doubles
   // own-plane chunk offsets
-  const int own_base = p * 128, own_sw = p & 7;
-  const int cp_dst0 = (t >> 3) * 128 + (((t & 7) ^ ((t >> 3) & 7)) << 4);
+  const int own_base = p * 128, own_sw = swz(p);
+  // chunk i = r*TT + t of a tile -> plane r*TT/8 + (t>>3), 16-byte unit t&7
+  auto cp_dst = [&](int r) -> int {
+    const int pi = r * (TT / 8) + (t >> 3);
+    return pi * 128 + (((t & 7) ^ swz(pi)) << 4);
+  };
   const bool group_full = (g * GE + GE <= G.nelem);
 
   auto issue = [&](int j) {
@@ -394,14 +467,13 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
     const int q0 = it * QI, nq = min(QI, Q - q0);
     const double* tsrc = src + cta_base + (size_t)q0 * GPL * 16 + t * 2;
     const unsigned sb = smem_u32 + (j % NBUF) * IN_BYTES;
-    // chunk i = r*TT + t -> plane r*TT/8 + (t>>3), 16-byte unit t&7: the swizzle term does not depend on r
     if (nq == QI) {
       TSE_UNROLL
-      for (int r = 0; r < 8; ++r) cp_async16(sb + cp_dst0 + r * (TT * 16), tsrc + r * (TT * 2));
+      for (int r = 0; r < 8; ++r) cp_async16(sb + cp_dst(r), tsrc + r * (TT * 2));
     } else {
       TSE_UNROLL
       for (int r = 0; r < 8; ++r)
-        if (r * (TT / 8) + (t >> 3) < nq * GPL) cp_async16(sb + cp_dst0 + r * (TT * 16), tsrc + r * (TT * 2));
+        if (r * (TT / 8) + (t >> 3) < nq * GPL) cp_async16(sb + cp_dst(r), tsrc + r * (TT * 2));
     }
     if (a.pending[which]) {
       TSE_UNROLL
@@ -444,6 +516,13 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
   const double cf = (OP == OP_STAGE3) ? a.visc_coef * a.dp0[k] : 0.0;
 
   double keep[16];  // STAGE3: cf*lap of the first item; TIME_AVG: Qdp(n0)
+  // limiter bounds of this thread's plane, fetched one tracer step of the loop ahead (a global load the math depends on)
+  const size_t pidx0 = (((size_t)g * NKC + kc) * Q + qi) * GPL + pl;
+  double minp_n = 0.0, maxp_n = 0.0;
+  if (kStage && evalid && qi < Q) {
+    minp_n = a.qmin[pidx0];
+    maxp_n = a.qmax[pidx0];
+  }
   issue(0);
   if (nitems > 1) issue(1);
   for (int j = 0; j < nitems; ++j) {
@@ -537,7 +616,11 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
         TSE_UNROLL
         for (int n = 0; n < 16; ++n) keep[n] = cf * lap[n];
       } else if (kStage) {
-        double minp = a.qmin[pidx], maxp = a.qmax[pidx];
+        double minp = minp_n, maxp = maxp_n;
+        if (evalid && q + QI < Q) {
+          minp_n = a.qmin[pidx + (size_t)QI * GPL];
+          maxp_n = a.qmax[pidx + (size_t)QI * GPL];
+        }
         if (OP == OP_STAGE2) {
           double mn0 = 1e300, mx0 = -1e300, mn1 = 1e300, mx1 = -1e300;
           TSE_UNROLL
@@ -576,7 +659,8 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
         }
         asm volatile("" ::: "memory");
 #ifndef TSE_SKIP_LIMITER
-        limiter_y(y, smem_u32 + (unsigned)(pp - smem) + (cfg.CL < 0 ? 0 : cfg.CL) * PP_BYTES + pl * 16, sumc, minp, maxp);
+        limiter_y(y, smem_u32 + (unsigned)(pp - smem) + (cfg.CL < 0 ? 0 : cfg.CL) * PP_BYTES + pl * 16,
+                  smem_u32 + (unsigned)(pp - smem) + (cfg.RC < 0 ? 0 : cfg.RC) * PP_BYTES + pl * 16, sumc, minp, maxp);
 #endif
         asm volatile("" ::: "memory");
         a.qmin[pidx] = minp;
@@ -596,13 +680,13 @@ __global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables 
       double* tdst = a.out + cta_base + (size_t)q0 * GPL * 16 + t * 2;
       if (nq == QI && group_full) {
         TSE_UNROLL
-        for (int r = 0; r < 8; ++r) *reinterpret_cast<double2*>(tdst + r * (TT * 2)) = lds128(outb, cp_dst0 + r * (TT * 16));
+        for (int r = 0; r < 8; ++r) *reinterpret_cast<double2*>(tdst + r * (TT * 2)) = lds128(outb, cp_dst(r));
       } else {
         TSE_UNROLL
         for (int r = 0; r < 8; ++r) {
           const int pi = r * (TT / 8) + (t >> 3);
           if (pi < nq * GPL && g * GE + ((pi / KC) % GE) < G.nelem)
-            *reinterpret_cast<double2*>(tdst + r * (TT * 2)) = lds128(outb, cp_dst0 + r * (TT * 16));
+            *reinterpret_cast<double2*>(tdst + r * (TT * 2)) = lds128(outb, cp_dst(r));
         }
       }
     }
