@@ -28,6 +28,7 @@
 #include "tse_kernels.cuh"
 #include "tse_remap.cuh"
 #include "tse_tile.cuh"
+#include "tse_pipe.cuh"
 #include "tse_dcmip.cuh"
 #include "tse_diag.cuh"
 
@@ -75,6 +76,7 @@ struct tse_state {
   // tracer buffers
   double* qbuf[4] = {nullptr, nullptr, nullptr, nullptr};
   double* qghost[4] = {nullptr, nullptr, nullptr, nullptr};  // halo of each buffer when it is pending (multi-GPU)
+  CUtensorMap qmap[4];  // TMA view of each buffer: rows = planes of 16 doubles, box = BOX_ROWS planes, SWIZZLE_128B
   size_t qdoubles = 0;
   int slot_buf[3] = {-1, 0, 1};     // [tl] (1-based) -> buffer
   int slot_pending[3] = {0, 0, 0};  // [tl] buffer holds pre-DSS values
@@ -304,12 +306,21 @@ void set_src(const tse_state* s, TileArgs& a, int i, int buf, int pending) {
   a.ghost[i] = s->qghost[buf];
   a.pending[i] = pending;
 }
+const CUtensorMap& map_of(const tse_state* s, const double* buf) {
+  for (int b = 0; b < 4; ++b)
+    if (s->qbuf[b] == buf) return s->qmap[b];
+  return s->qmap[0];
+}
 template <int OP>
 void launch_tile(tse_state* s, TileArgs a, const int* glist = nullptr, int ngl = 0) {
   a.glist = glist;
   const int ng = glist ? ngl : s->ngroups;
   if (ng == 0) return;
-  k_tile<OP><<<ng * NKC, TT, tile_smem_bytes(OP, s->tiles.hmax), s->stream>>>(s->geo, s->dvv, s->tiles, a);
+  PipeMaps pm;
+  pm.in[0] = map_of(s, a.src[0]);
+  pm.in[1] = map_of(s, a.src[1] ? a.src[1] : a.src[0]);
+  pm.out = map_of(s, a.out ? a.out : a.src[0]);
+  k_pipe<OP><<<ng * NKC, PT, pipe_smem_bytes(OP, s->tiles.hmax), s->stream>>>(pm, s->geo, s->dvv, s->tiles, a);
   ++s->launches;
 }
 // producer launch of a field whose boundary nodes are exchanged: boundary groups, then (after `start_comm` queued the pack and
@@ -569,7 +580,7 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
     int *d_a, *d_b, *d_c;
     if (upload(s, &d_a, gsrc_t) || upload(s, &d_b, halo_off) || upload(s, &d_c, halo_src)) return 1;
     s->tiles.gsrc_t = d_a; s->tiles.halo_off = d_b; s->tiles.halo_src = d_c; s->tiles.hmax = hmax;
-    if (tile_smem_bytes(OP_STAGE2, hmax) > 227 * 1024 || tile_smem_bytes(OP_STAGE3, hmax) > 227 * 1024)
+    if (pipe_smem_bytes(OP_STAGE2, hmax) > 227 * 1024 || pipe_smem_bytes(OP_STAGE3, hmax) > 227 * 1024)
       return fail("tse_init: halo of %d nodes per group does not fit in shared memory", hmax);
     if (tile_in_bytes(hmax) / 8 >= 65536) return fail("tse_init: halo of %d nodes per group overflows the gather offsets", hmax);
   }
@@ -610,6 +621,25 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
   if (s->qdoubles >= ((size_t)1 << 35)) return fail("tse_init: tracer field too large for one GPU (%zu doubles)", s->qdoubles);
   for (int b = 0; b < 4; ++b)
     if (dalloc(s, &s->qbuf[b], s->qdoubles)) return 1;
+  {
+    // tensor maps for the TMA tile loads/stores of k_pipe (driver entry point resolved through the runtime: no -lcuda)
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail("tse_init: cuTensorMapEncodeTiled is not available in this driver");
+    const cuuint64_t gdim[2] = {16, (cuuint64_t)(s->qdoubles / 16)};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {16, (cuuint32_t)BOX_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int b = 0; b < 4; ++b) {
+      const CUresult r = ((EncodeTiled)fn)(&s->qmap[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, s->qbuf[b], gdim, gstride, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail("tse_init: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
+  }
   if (dalloc(s, &s->vn0, 2 * s->ldoubles) || dalloc(s, &s->dp, s->ldoubles) || dalloc(s, &s->divdp, s->ldoubles) ||
       dalloc(s, &s->divdp_proj, s->ldoubles) || dalloc(s, &s->eta_dot, s->ldoubles) || dalloc(s, &s->omega_p, s->ldoubles) ||
       dalloc(s, &s->lev_tmp, s->ldoubles) || dalloc(s, &s->dp3d, s->ldoubles) || dalloc(s, &s->ps_v, (size_t)s->npad * 16))
@@ -634,13 +664,15 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
   }
   CU(cudaFuncSetAttribute(k_vertical_remap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RM_SMEM));
   const int hm = s->tiles.hmax;
-  CU(cudaFuncSetAttribute(k_tile<OP_MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_MINMAX, hm)));
-  CU(cudaFuncSetAttribute(k_tile<OP_STAGE1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_STAGE1, hm)));
-  CU(cudaFuncSetAttribute(k_tile<OP_STAGE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_STAGE2, hm)));
-  CU(cudaFuncSetAttribute(k_tile<OP_STAGE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_STAGE3, hm)));
-  CU(cudaFuncSetAttribute(k_tile<OP_BIHARM_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_BIHARM_PRE, hm)));
-  CU(cudaFuncSetAttribute(k_tile<OP_TIME_AVG>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_TIME_AVG, hm)));
-  CU(cudaFuncSetAttribute(k_tile<OP_RESOLVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes(OP_RESOLVE, hm)));
+#define TSE_TILE_SMEM(OP) CU(cudaFuncSetAttribute(k_pipe<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem_bytes(OP, hm)))
+  TSE_TILE_SMEM(OP_MINMAX);
+  TSE_TILE_SMEM(OP_STAGE1);
+  TSE_TILE_SMEM(OP_STAGE2);
+  TSE_TILE_SMEM(OP_STAGE3);
+  TSE_TILE_SMEM(OP_BIHARM_PRE);
+  TSE_TILE_SMEM(OP_TIME_AVG);
+  TSE_TILE_SMEM(OP_RESOLVE);
+#undef TSE_TILE_SMEM
   CU(cudaStreamSynchronize(s->stream));
   *out = s;
   return 0;

@@ -1,0 +1,464 @@
+// Tiled tracer-field kernels (sm_100a), warp-specialised: the element operators, limiter, package and tile layout are in
+// tse_tile.cuh; this file is the pipeline around them.
+//
+//   producer warp   moves everything that comes from HBM.  Per pipeline item (QI tracers of one input field) it issues the
+//                   tile as TMA tensor copies (cp.async.bulk.tensor.2d, 16 planes x 128 B per box, SWIZZLE_128B = the XOR
+//                   swizzle the plane-per-thread reads need) and the DSS halo (68 x KC scattered nodes per tracer for a 4x4
+//                   patch) as 8-byte cp.async; both complete on the stage's "full" mbarrier (complete_tx bytes /
+//                   cp.async.mbarrier.arrive.noinc).  It runs up to NST items ahead of the math and never touches registers
+//                   the math needs.
+//   consumer warps  (TT threads, one 4x4 plane per thread) wait on "full", pull their plane and its DSS neighbours into
+//                   registers, release the stage at once ("empty" mbarrier, one arrive per thread), do the arithmetic, stage
+//                   the result in the OUT tile and hand it to a TMA store (one 2 KB box per tracer per warp, bulk async
+//                   group per warp).  There is no CTA-wide barrier in the steady state: a warp that sits in a long limiter
+//                   loop delays nobody until the pipeline runs dry.
+//
+// Rows of the tensor maps are planes (16 doubles) of a tracer field in layout order, so a tile is a run of consecutive rows.
+#pragma once
+#include <cuda.h>
+
+#include "tse_tile.cuh"
+
+namespace tse {
+
+#ifndef TSE_NST
+#define TSE_NST 2
+#endif
+constexpr int NST = TSE_NST;             // IN stages
+constexpr int NCW = TT / 32;             // consumer warps
+constexpr int PT = TT + 32;              // threads per CTA: consumers + one producer warp
+constexpr int BOX_ROWS = EPW * KC;       // planes per TMA box = one warp's planes of one tracer
+static_assert(BOX_ROWS == 16 && GPL % BOX_ROWS == 0, "TMA box = 16 planes");
+static_assert(EPW > 1, "SWIZZLE_128B is the row&7 XOR");
+
+__host__ __device__ constexpr int pipe_in_stride(int hmax) { return (tile_in_bytes(hmax) + 1023) & ~1023; }
+__host__ __device__ constexpr int pipe_smem_bytes(int op, int hmax) {
+  return 1024 + NST * pipe_in_stride(hmax) + (tile_cfg(op).has_out ? TILE_BYTES : 0) + tile_cfg(op).npp * PP_BYTES +
+         tile_cfg(op).nel * EL_BYTES + hmax * KC * 10 + 16 + 2 * NST * 8;
+}
+
+struct PipeMaps {
+  CUtensorMap in[2];  // the two input fields (box = BOX_ROWS planes)
+  CUtensorMap out;
+};
+
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(addr) : "memory");
+}
+// arrive with an explicit count (always 1): `dep` is OR-ed in through a runtime zero, which makes the arrive wait for the
+// registers `dep` was computed from (see the stage release in k_pipe)
+__device__ __forceinline__ void mbar_arrive_after(unsigned addr, unsigned dep, unsigned zero) {
+  const unsigned cnt = 1u | (dep & zero);
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;\n" ::"r"(addr), "r"(cnt) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned addr, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+// completion of all cp.async issued so far by this thread counts as one (pre-counted) arrival on the mbarrier
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(unsigned addr) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned mbar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, unsigned src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(map), "r"(c0), "r"(c1), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;\n" ::"n"(TT) : "memory"); }
+
+template <int OP>
+__global__ void __launch_bounds__(PT, TSE_MINB) k_pipe(const __grid_constant__ PipeMaps maps, Geo G, Dvv D, TileTables tb, TileArgs a) {
+  constexpr TileCfg cfg = tile_cfg(OP);
+  constexpr bool kStage = (OP == OP_STAGE1 || OP == OP_STAGE2 || OP == OP_STAGE3);
+  constexpr int NIN = (OP == OP_STAGE3 || OP == OP_TIME_AVG) ? 2 : 1;
+  constexpr bool kHasOut = cfg.has_out != 0;
+  extern __shared__ unsigned char smem_raw[];
+  const unsigned raw_u32 = (unsigned)__cvta_generic_to_shared(smem_raw);
+  unsigned char* const smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);  // SWIZZLE_128B tiles sit on 1 KB boundaries
+  const unsigned smem_u32 = (unsigned)__cvta_generic_to_shared(smem);
+  const int IN_STRIDE = pipe_in_stride(tb.hmax);
+  unsigned char* const outb = smem + NST * IN_STRIDE;
+  unsigned char* const pp = outb + (kHasOut ? TILE_BYTES : 0);
+  unsigned char* const elb = pp + cfg.npp * PP_BYTES;
+  long long* const htab = reinterpret_cast<long long*>(elb + cfg.nel * EL_BYTES);  // halo sources (double index, tracer 0)
+  unsigned short* const hdtab = reinterpret_cast<unsigned short*>(htab + tb.hmax * KC);  // halo destinations (8-byte units)
+  const unsigned bar_u32 = (smem_u32 + (unsigned)(reinterpret_cast<unsigned char*>(hdtab + tb.hmax * KC) - smem) + 15u) & ~15u;
+  const int ZERO_OFF = TILE_BYTES + QI * tb.hmax * KC * 8;
+  auto full_bar = [&](int b) -> unsigned { return bar_u32 + b * 8; };
+  auto empty_bar = [&](int b) -> unsigned { return bar_u32 + (NST + b) * 8; };
+
+  const int t = threadIdx.x;
+  const int g = a.glist ? a.glist[blockIdx.x / NKC] : blockIdx.x / NKC, kc = blockIdx.x % NKC;
+  const int w = t >> 5, lane = t & 31;
+  const int Q = a.Q;
+  const int nit = (Q + QI - 1) / QI;
+  const int nitems = nit * NIN;
+  const unsigned row0 = (unsigned)(((size_t)g * NKC + kc) * Q * GPL);  // tensor-map row of (tracer 0, plane 0) of this CTA
+
+  if (t == 0) {
+    for (int b = 0; b < NST; ++b) {
+      mbar_init(full_bar(b), 1 + 32);  // expect_tx arrive of the issuing lane + one cp.async arrival per producer lane
+      mbar_init(empty_bar(b), TT);  // every consumer thread releases for itself
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (t < NST) *reinterpret_cast<double*>(smem + t * IN_STRIDE + ZERO_OFF) = 0.0;
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  if (w == NCW) {
+    // =============================================== producer warp ===============================================
+    const int hoff = tb.halo_off[g], H = tb.halo_off[g + 1] - hoff;
+    const int nhalo = H * KC;
+    const bool any_pending = a.pending[0] || (NIN == 2 && a.pending[1]);
+    if (any_pending) {
+      for (int idx = lane; idx < nhalo; idx += 32) {  // entry idx -> (h = idx % H, kk2 = idx / H), h fastest
+        const int h = idx % H, kk2 = idx / H;
+        const int code = tb.halo_src[hoff + h];
+        const int kq = kc * KC + kk2;
+        htab[idx] = code >= 0 ? (long long)(qplane(code >> 4, 0, kq, Q) * 16 + (code & 15)) : -((long long)(-code - 2) * Q * NLEV + kq) - 1;
+        hdtab[idx] = (unsigned short)((TILE_BYTES + (h * KC + kk2) * 8) >> 3);
+      }
+      __syncwarp();
+    }
+    for (int j = 0; j < nitems; ++j) {
+      const int b = j % NST, it = j / NIN, which = j % NIN;
+      const int q0 = it * QI, nq = min(QI, Q - q0);
+      if (j >= NST) mbar_wait(empty_bar(b), (unsigned)(((j / NST) - 1) & 1));
+      const unsigned sb = smem_u32 + b * IN_STRIDE;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(full_bar(b), (unsigned)(nq * GPL * 128));
+        const CUtensorMap* m = &maps.in[which];
+        const int r0 = (int)(row0 + (unsigned)q0 * GPL);
+        for (int bx = 0; bx < nq * (GPL / BOX_ROWS); ++bx) tma_load_2d(sb + bx * (BOX_ROWS * 128), m, 0, r0 + bx * BOX_ROWS, full_bar(b));
+      }
+      if (a.pending[which]) {
+        const double* src = a.src[which];
+        const double* ghost = a.ghost[which];
+        for (int idx = lane; idx < nhalo; idx += 32) {
+          const long long v = htab[idx];
+          const unsigned dst = sb + ((unsigned)hdtab[idx] << 3);
+          for (int qi2 = 0; qi2 < nq; ++qi2) {
+            const double* gp = v >= 0 ? src + v + (size_t)(q0 + qi2) * GPL * 16 : ghost + (-(v + 1)) + (size_t)(q0 + qi2) * NLEV;
+            cp_async8(dst + qi2 * tb.hmax * KC * 8, gp);
+          }
+        }
+      }
+      cp_async_mbar_arrive_noinc(full_bar(b));
+    }
+    return;
+  }
+
+  // ================================================= consumer warps =================================================
+  const int kk = lane & 3, el = EPW * (w % (GE / EPW)) + ((lane >> 2) % EPW), qi = QW * (w / (GE / EPW)) + (lane >> 2) / EPW;
+  const int pl = el * KC + kk;   // plane within one tracer's tile
+  const int p = qi * GPL + pl;   // plane within the QI-tracer tile
+  const int e = g * GE + el, k = kc * KC + kk;
+  const bool evalid = e < G.nelem;
+
+  // ---- level package (see tse_tile.cuh) ------------------------------------------------------------------------------
+  const bool main_pending = (OP == OP_STAGE3) ? (a.pending[1] != 0) : (a.pending[0] != 0);
+  if (cfg.nel > 0 && t < GE * 8) {
+    const int pe = t >> 3, c = t & 7, ee = g * GE + pe;
+    double2 e1 = make_double2(0, 0), e2 = e1, rs = e1, t11 = e1, t12 = e1, t22 = e1;
+    if (ee < G.nelem) {
+      const size_t b = (size_t)ee * 16 + 2 * c;
+      const double2 sp = *reinterpret_cast<const double2*>(G.spheremp + b);
+      rs = *reinterpret_cast<const double2*>(G.rspheremp + b);
+      const double2 rm = *reinterpret_cast<const double2*>(G.rmr + b);
+      const double rx0 = main_pending ? rs.x : 1.0, rx1 = main_pending ? rs.y : 1.0;
+      e1 = make_double2(sp.x * rx0, sp.y * rx1);
+      e2 = make_double2(a.dt * (sp.x * rm.x), a.dt * (sp.y * rm.y));
+      if (cfg.T11 >= 0) {
+        const double* T = G.T + (size_t)ee * 48 + 2 * c;
+        t11 = *reinterpret_cast<const double2*>(T);
+        t12 = *reinterpret_cast<const double2*>(T + 16);
+        t22 = *reinterpret_cast<const double2*>(T + 32);
+      }
+    }
+    const int off = (c * GE + pe) * 16;
+    if (cfg.E1 >= 0) *reinterpret_cast<double2*>(elb + cfg.E1 * EL_BYTES + off) = e1;
+    if (cfg.E2 >= 0) *reinterpret_cast<double2*>(elb + cfg.E2 * EL_BYTES + off) = e2;
+    if (cfg.RSPH >= 0) *reinterpret_cast<double2*>(elb + cfg.RSPH * EL_BYTES + off) = rs;
+    if (cfg.T11 >= 0) {
+      *reinterpret_cast<double2*>(elb + cfg.T11 * EL_BYTES + off) = t11;
+      *reinterpret_cast<double2*>(elb + cfg.T12 * EL_BYTES + off) = t12;
+      *reinterpret_cast<double2*>(elb + cfg.T22 * EL_BYTES + off) = t22;
+    }
+  }
+  if (cfg.npp > 0) {
+    constexpr int PARTS = TT / GPL;
+    const int ppl = t / PARTS, part = t % PARTS;
+    const int pe = g * GE + ppl / KC, pk = kc * KC + ppl % KC;
+    TSE_UNROLL
+    for (int cc = 0; cc < 8 / PARTS; ++cc) {
+      const int c = part * (8 / PARTS) + cc, n = 2 * c;
+      double2 u1 = make_double2(0, 0), u2 = u1, cl = make_double2(1, 1), rd = make_double2(1, 1), rcl = make_double2(1, 1);
+      if (pe < G.nelem) {
+        const size_t lp = lplane(pe, pk) * 16 + n, gb = (size_t)pe * 16 + n;
+        const double2 dpv = *reinterpret_cast<const double2*>(a.dp + lp);
+        const double2 dj = *reinterpret_cast<const double2*>(a.divdp_proj + lp);
+        const double2 rs = *reinterpret_cast<const double2*>(G.rspheremp + gb);
+        const double rx0 = main_pending ? rs.x : 1.0, rx1 = main_pending ? rs.y : 1.0;
+        const double dps0 = dpv.x - a.rhs_mult_dt * dj.x, dps1 = dpv.y - a.rhs_mult_dt * dj.y;
+        const double r0 = 1.0 / dps0, r1 = 1.0 / dps1;
+        rd = make_double2(r0 * rx0, r1 * rx1);
+        if (kStage) {
+          const double2 dd = *reinterpret_cast<const double2*>(a.divdp + lp);
+          const double2 v1 = *reinterpret_cast<const double2*>(a.vn0 + vplane(pe, pk, 0) * 16 + n);
+          const double2 v2 = *reinterpret_cast<const double2*>(a.vn0 + vplane(pe, pk, 1) * 16 + n);
+          const double2 sp = *reinterpret_cast<const double2*>(G.spheremp + gb);
+          const double* mD = G.mD + (size_t)pe * 64 + n;
+          const double2 m11 = *reinterpret_cast<const double2*>(mD), m12 = *reinterpret_cast<const double2*>(mD + 16);
+          const double2 m21 = *reinterpret_cast<const double2*>(mD + 32), m22 = *reinterpret_cast<const double2*>(mD + 48);
+          const double vs10 = v1.x * r0, vs11 = v1.y * r1, vs20 = v2.x * r0, vs21 = v2.y * r1;
+          u1 = make_double2((m11.x * vs10 + m12.x * vs20) * rx0, (m11.y * vs11 + m12.y * vs21) * rx1);
+          u2 = make_double2((m21.x * vs10 + m22.x * vs20) * rx0, (m21.y * vs11 + m22.y * vs21) * rx1);
+          cl = make_double2(sp.x * (dps0 - a.dt * dd.x), sp.y * (dps1 - a.dt * dd.y));
+          rcl = make_double2(1.0 / cl.x, 1.0 / cl.y);
+        }
+      }
+      const int off = (c * GPL + ppl) * 16;
+      if (cfg.U1 >= 0) *reinterpret_cast<double2*>(pp + cfg.U1 * PP_BYTES + off) = u1;
+      if (cfg.U2 >= 0) *reinterpret_cast<double2*>(pp + cfg.U2 * PP_BYTES + off) = u2;
+      if (cfg.CL >= 0) *reinterpret_cast<double2*>(pp + cfg.CL * PP_BYTES + off) = cl;
+      if (cfg.RDP >= 0) *reinterpret_cast<double2*>(pp + cfg.RDP * PP_BYTES + off) = rd;
+      if (cfg.RC >= 0) *reinterpret_cast<double2*>(pp + cfg.RC * PP_BYTES + off) = rcl;
+    }
+  }
+
+  // ---- per-thread DSS gather offsets (bytes inside an IN stage), two 16-bit offsets (8-byte units) per register ---------
+  unsigned goff[NSLOT / 2];
+  {
+    const int* gs = tb.gsrc_t + (size_t)(evalid ? e : 0) * NSLOT;
+    TSE_UNROLL
+    for (int s = 0; s < NSLOT; ++s) {
+      const int code = evalid ? gs[s] : -1;
+      int off = ZERO_OFF;
+      if (code >= 256) off = TILE_BYTES + ((qi * tb.hmax + (code - 256)) * KC + kk) * 8;
+      else if (code >= 0) {
+        const int p2 = qi * GPL + (code >> 4) * KC + kk, node = code & 15;
+        off = p2 * 128 + ((((node >> 1) ^ swz(p2))) << 4) + (node & 1) * 8;
+      }
+      if (s & 1) goff[s >> 1] |= (unsigned)(off >> 3) << 16;
+      else goff[s >> 1] = (unsigned)(off >> 3);
+    }
+  }
+  auto gofs = [&](int s) -> int { return (int)(((s & 1) ? (goff[s >> 1] >> 16) : (goff[s >> 1] & 0xffffu)) << 3); };
+
+  const int own_base = p * 128, own_sw = swz(p);
+  // this warp's planes of tracer slot q2 are rows q2*GPL + wrow .. +BOX_ROWS-1 of the tile
+  const int wrow = BOX_ROWS * (w % (GE / EPW)), wq0 = QW * (w / (GE / EPW));
+
+  double sumc = 0.0;
+  consumer_barrier();  // package visible to all consumer warps
+  if (kStage) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    TSE_UNROLL
+    for (int c = 0; c < 8; c += 2) {
+      const double2 x0 = lds128(pp + cfg.CL * PP_BYTES, (c * GPL + pl) * 16);
+      const double2 x1 = lds128(pp + cfg.CL * PP_BYTES, ((c + 1) * GPL + pl) * 16);
+      s0 += x0.x; s1 += x0.y; s2 += x1.x; s3 += x1.y;
+    }
+    sumc = (s0 + s1) + (s2 + s3);
+  }
+  const double cf = (OP == OP_STAGE3) ? a.visc_coef * a.dp0[k] : 0.0;
+
+  double keep[16];  // STAGE3: cf*lap of the first item; TIME_AVG: Qdp(n0)
+  // limiter bounds of this thread's plane, fetched one tracer step of the loop ahead (a global load the math depends on)
+  const size_t pidx0 = (((size_t)g * NKC + kc) * Q + qi) * GPL + pl;
+  double minp_n = 0.0, maxp_n = 0.0;
+  if (kStage && evalid && qi < Q) {
+    minp_n = a.qmin[pidx0];
+    maxp_n = a.qmax[pidx0];
+  }
+  for (int j = 0; j < nitems; ++j) {
+    const int b = j % NST;
+    mbar_wait(full_bar(b), (unsigned)((j / NST) & 1));
+    const unsigned char* inb = smem + b * IN_STRIDE;
+    const int it = j / NIN, which = j % NIN;
+    const int q = it * QI + qi;
+    const bool valid = evalid && q < Q;
+    const size_t pidx = pidx0 + (size_t)it * QI * GPL;  // global plane index
+
+    double S[16];
+    TSE_UNROLL
+    for (int c = 0; c < 8; ++c) {
+      const double2 v = lds128(inb, own_base + ((c ^ own_sw) << 4));
+      S[2 * c] = v.x;
+      S[2 * c + 1] = v.y;
+    }
+    if (a.pending[which]) {  // DSS in the reference's unpack order: S, E, N, W edges, then SW, SE, NE, NW corners
+      TSE_UNROLL
+      for (int i = 0; i < 4; ++i) S[i] += lds64(inb, gofs(i));
+      TSE_UNROLL
+      for (int i = 0; i < 4; ++i) S[3 + 4 * i] += lds64(inb, gofs(4 + i));
+      TSE_UNROLL
+      for (int i = 0; i < 4; ++i) S[12 + i] += lds64(inb, gofs(8 + i));
+      TSE_UNROLL
+      for (int i = 0; i < 4; ++i) S[4 * i] += lds64(inb, gofs(12 + i));
+      S[0] += lds64(inb, gofs(16));
+      S[3] += lds64(inb, gofs(17));
+      S[15] += lds64(inb, gofs(18));
+      S[12] += lds64(inb, gofs(19));
+    }
+    {
+      // Release the stage as soon as this thread's copies sit in registers.  The arrive must not overtake the loads: an LDS
+      // that is still in flight when the producer's refill lands reads the next item (seen on the GPU as rare wrong planes at
+      // ne120), so the arrive is made to depend on every loaded register.
+      unsigned dep = 0;
+      TSE_UNROLL
+      for (int n = 0; n < 16; ++n) dep ^= (unsigned)__double2hiint(S[n]);
+      mbar_arrive_after(empty_bar(b), dep, (unsigned)a.zero);
+    }
+
+    const bool last_of_iter = (which == NIN - 1);
+    if (valid) {
+      if (OP == OP_MINMAX || OP == OP_BIHARM_PRE) {
+        TSE_UNROLL
+        for (int c = 0; c < 8; ++c) {
+          const double2 rd = lds128(pp + cfg.RDP * PP_BYTES, (c * GPL + pl) * 16);
+          S[2 * c] *= rd.x;
+          S[2 * c + 1] *= rd.y;
+        }
+        double mn0 = dmin(S[0], S[1]), mx0 = dmax(S[0], S[1]), mn1 = dmin(S[2], S[3]), mx1 = dmax(S[2], S[3]);
+        TSE_UNROLL
+        for (int n = 4; n < 16; n += 4) {
+          mn0 = dmin(mn0, dmin(S[n], S[n + 1]));
+          mx0 = dmax(mx0, dmax(S[n], S[n + 1]));
+          mn1 = dmin(mn1, dmin(S[n + 2], S[n + 3]));
+          mx1 = dmax(mx1, dmax(S[n + 2], S[n + 3]));
+        }
+        a.qmin_loc[pidx] = dmin(mn0, mn1);
+        a.qmax_loc[pidx] = dmax(mx0, mx1);
+        if (OP == OP_BIHARM_PRE) {
+          double lap[16];
+          laplace_wk_el(S, D, elb + cfg.T11 * EL_BYTES, elb + cfg.T12 * EL_BYTES, elb + cfg.T22 * EL_BYTES, el, lap);
+          TSE_UNROLL
+          for (int n = 0; n < 16; ++n) S[n] = lap[n];
+        }
+      } else if (OP == OP_RESOLVE) {
+        TSE_UNROLL
+        for (int c = 0; c < 8; ++c) {
+          const double2 rs = lds128(elb + cfg.RSPH * EL_BYTES, (c * GE + el) * 16);
+          S[2 * c] *= rs.x;
+          S[2 * c + 1] *= rs.y;
+        }
+      } else if (OP == OP_TIME_AVG) {
+        if (which == 0) {
+          TSE_UNROLL
+          for (int n = 0; n < 16; ++n) keep[n] = S[n];
+        } else {
+          TSE_UNROLL
+          for (int c = 0; c < 8; ++c) {
+            double2 rs = lds128(elb + cfg.RSPH * EL_BYTES, (c * GE + el) * 16);
+            if (!a.pending[1]) rs = make_double2(1.0, 1.0);
+            S[2 * c] = (keep[2 * c] + (a.rkstage - 1.0) * (rs.x * S[2 * c])) / a.rkstage;
+            S[2 * c + 1] = (keep[2 * c + 1] + (a.rkstage - 1.0) * (rs.y * S[2 * c + 1])) / a.rkstage;
+          }
+        }
+      } else if (OP == OP_STAGE3 && which == 0) {
+        // second half of biharmonic_wk_scalar_minmax: lap(rspheremp*DSS(qtens)); Qtens_biharmonic*spheremp = cf*lap
+        TSE_UNROLL
+        for (int c = 0; c < 8; ++c) {
+          const double2 rs = lds128(elb + cfg.RSPH * EL_BYTES, (c * GE + el) * 16);
+          S[2 * c] *= rs.x;
+          S[2 * c + 1] *= rs.y;
+        }
+        double lap[16];
+        laplace_wk_el(S, D, elb + cfg.T11 * EL_BYTES, elb + cfg.T12 * EL_BYTES, elb + cfg.T22 * EL_BYTES, el, lap);
+        TSE_UNROLL
+        for (int n = 0; n < 16; ++n) keep[n] = cf * lap[n];
+      } else if (kStage) {
+        double minp = minp_n, maxp = maxp_n;
+        if (q + QI < Q) {
+          minp_n = a.qmin[pidx + (size_t)QI * GPL];
+          maxp_n = a.qmax[pidx + (size_t)QI * GPL];
+        }
+        if (OP == OP_STAGE2) {
+          double mn0 = 1e300, mx0 = -1e300, mn1 = 1e300, mx1 = -1e300;
+          TSE_UNROLL
+          for (int c = 0; c < 8; ++c) {
+            const double2 rd = lds128(pp + cfg.RDP * PP_BYTES, (c * GPL + pl) * 16);
+            const double q0v = S[2 * c] * rd.x, q1v = S[2 * c + 1] * rd.y;
+            mn0 = dmin(mn0, q0v);
+            mx0 = dmax(mx0, q0v);
+            mn1 = dmin(mn1, q1v);
+            mx1 = dmax(mx1, q1v);
+          }
+          minp = dmin(minp, dmin(mn0, mn1));
+          maxp = dmax(maxp, dmax(mx0, mx1));
+        }
+        double y[16];
+        asm volatile("" ::: "memory");
+        flux_div(S, pp + cfg.U1 * PP_BYTES, pp + cfg.U2 * PP_BYTES, pl, D, y);
+        asm volatile("" ::: "memory");
+        const unsigned e1a = smem_u32 + (unsigned)(elb - smem) + (cfg.E1 < 0 ? 0 : cfg.E1) * EL_BYTES + el * 16;
+        const unsigned e2a = smem_u32 + (unsigned)(elb - smem) + (cfg.E2 < 0 ? 0 : cfg.E2) * EL_BYTES + el * 16;
+        TSE_UNROLL
+        for (int c = 0; c < 8; ++c) {
+          const double2 e1 = lds128v(e1a + c * GE * 16);
+          const double2 e2 = lds128v(e2a + c * GE * 16);
+          y[2 * c] = fma(-e2.x, y[2 * c], e1.x * S[2 * c]);
+          y[2 * c + 1] = fma(-e2.y, y[2 * c + 1], e1.y * S[2 * c + 1]);
+          if (OP == OP_STAGE3) {
+            y[2 * c] += keep[2 * c];
+            y[2 * c + 1] += keep[2 * c + 1];
+          }
+        }
+        asm volatile("" ::: "memory");
+#ifndef TSE_SKIP_LIMITER
+        limiter_y(y, smem_u32 + (unsigned)(pp - smem) + (cfg.CL < 0 ? 0 : cfg.CL) * PP_BYTES + pl * 16,
+                  smem_u32 + (unsigned)(pp - smem) + (cfg.RC < 0 ? 0 : cfg.RC) * PP_BYTES + pl * 16, sumc, minp, maxp);
+#endif
+        asm volatile("" ::: "memory");
+        a.qmin[pidx] = minp;
+        a.qmax[pidx] = maxp;
+        TSE_UNROLL
+        for (int n = 0; n < 16; ++n) S[n] = y[n];
+      }
+    }
+
+    if (kHasOut && last_of_iter) {
+      // the previous store of this warp must have finished reading its OUT rows
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      TSE_UNROLL
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<double2*>(outb + own_base + ((c ^ own_sw) << 4)) = make_double2(S[2 * c], S[2 * c + 1]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const int q0 = it * QI;
+        for (int q2 = wq0; q2 < wq0 + QW && q0 + q2 < Q; ++q2)
+          tma_store_2d(&maps.out, 0, (int)(row0 + (unsigned)(q0 + q2) * GPL) + wrow, smem_u32 + (unsigned)(outb - smem) + (q2 * GPL + wrow) * 128);
+        bulk_commit();
+      }
+    }
+  }
+  if (kHasOut && lane == 0) bulk_wait0();
+}
+
+}  // namespace tse

@@ -1,14 +1,10 @@
-// Tiled tracer-field kernels (sm_100a): the production versions of the plane-per-thread kernels in tse_kernels.cuh.
+// Building blocks of the tiled tracer-field kernels (sm_100a); the kernel itself (k_pipe) is in tse_pipe.cuh.
 //
-// CTA = (group of 16 elements, chunk of 4 levels), QI*64 threads; it walks all tracers, QI at a time.  For each step the
-// QI*8 KB tile [q][el][kk][16] (contiguous in HBM) is copied with coalesced 16-byte cp.async into shared memory (IN buffer),
-// XOR-swizzled per 128-byte plane so that a thread can read "its" plane with conflict-free 128-bit loads.  One thread owns
-// one plane: all 4x4 contractions, the limiter and the extrema are register-only.  As soon as every thread has pulled its
-// plane (and its DSS neighbours) into registers the next tile is prefetched into the same IN buffer, overlapping the whole
-// compute phase; results are staged in a second (OUT) buffer and written back with coalesced 16-byte stores.
-//
-// A warp holds 8/QI elements x 4 levels x QI tracers, so that the data-dependent limiter loop diverges as little as possible
-// (the behaviour of a plane is mostly a property of its element).
+// CTA = (group of 16 elements, chunk of 4 levels); it walks all tracers, QI at a time.  For each step the QI*8 KB tile
+// [q][el][kk][16] (contiguous in HBM) lands in shared memory XOR-swizzled per 128-byte plane, so that a thread can read "its"
+// plane with conflict-free 128-bit loads.  One thread owns one plane: all 4x4 contractions, the limiter and the extrema are
+// register-only.  A warp holds 8/QI elements x 4 levels x QI tracers, so that the data-dependent limiter loop diverges as
+// little as possible (the behaviour of a plane is mostly a property of its element).
 //
 // DSS (edgeVpack / bndry_exchangeV / edgeVunpack, edge_mod.F90:366-742) is fused into the load of the consumer: a field is
 // stored "pre-DSS" (spheremp-weighted); neighbours inside the group are read straight from the tile in shared memory,
@@ -20,8 +16,8 @@
 //   dp_s = dp - rhs_mult*dt*divdp_proj, Vstar = vn0/dp_s, dp_star = dp_s - dt*divdp        (prim_advection_mod.F90:753,847-864)
 //   U_c  = rX * metdet*(Dinv(c,1)*Vstar1 + Dinv(c,2)*Vstar2)      gv_c = U_c * S       (S = raw DSS sum)
 //   E1   = spheremp*rX, E2 = dt*spheremp*rmetdet*rrearth          y = spheremp*Qtens = E1*S - E2*div
-//   CL   = spheremp*dp_star  (the limiter's c), RDP = rX/dp_s     (Q = S*RDP for the extrema)
-// The limiter works on y = c*x directly (limiter_y), so neither 1/dp_star nor the final spheremp multiply is needed.
+//   CL   = spheremp*dp_star  (the limiter's c), RC = 1/CL, RDP = rX/dp_s     (Q = S*RDP for the extrema)
+// The limiter works on y = c*x (limiter_y), so neither 1/dp_star nor the final spheremp multiply is needed on its fast path.
 #pragma once
 #include "tse_kernels.cuh"
 
@@ -36,7 +32,6 @@ namespace tse {
 constexpr int QI = TSE_QI;             // tracers per pipeline step
 constexpr int TT = QI * GPL;           // threads per CTA (256 for QI = 4)
 constexpr int TILE_BYTES = TT * 128;   // 32 KB for QI = 4
-constexpr int HPRE = 512 / TT;         // halo entries per thread resolved before the tracer loop (covers hmax <= 128)
 constexpr int QW = QI < 8 ? QI : 8;    // tracers per warp
 constexpr int EPW = 8 / QW;            // elements per warp (1 for QI >= 8: the limiter's work is a property of the element)
 static_assert(KC == 4 && (QI % QW) == 0 && (GE % EPW) == 0 && TT % 32 == 0 && TT <= 512, "warp mapping");
@@ -65,6 +60,7 @@ struct TileArgs {
   const double* dp0;
   double *qmin, *qmax, *qmin_loc, *qmax_loc;
   int Q;
+  int zero;          // always 0 (a value the compiler cannot fold: see mbar_arrive_after in tse_pipe.cuh)
   const int* glist;  // optional list of groups this launch covers (boundary groups first, interior groups while the halo is in flight)
 };
 
@@ -86,20 +82,10 @@ __host__ __device__ constexpr TileCfg tile_cfg(int op) {
                              : TileCfg{0, 1, 1, -1, -1, -1, -1, -1, -1, -1, 0, -1, -1, -1};
 }
 __host__ __device__ constexpr int tile_in_bytes(int hmax) { return TILE_BYTES + QI * hmax * KC * 8 + 16; }
-constexpr int NBUF = 2;  // IN buffers: two tiles are in flight while a third is being processed from registers
-__host__ __device__ constexpr int tile_smem_bytes(int op, int hmax) {
-  return NBUF * tile_in_bytes(hmax) + (tile_cfg(op).has_out ? TILE_BYTES : 0) + tile_cfg(op).npp * PP_BYTES + tile_cfg(op).nel * EL_BYTES;
-}
 
-__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
-}
 __device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;\n" ::); }
 
 __device__ __forceinline__ double2 lds128(const unsigned char* base, int off) { return *reinterpret_cast<const double2*>(base + off); }
 __device__ __forceinline__ double lds64(const unsigned char* base, int off) { return *reinterpret_cast<const double*>(base + off); }
@@ -306,389 +292,6 @@ __device__ __forceinline__ void laplace_wk_el(const double (&s)[16], const Dvv& 
         if (!(j == nn && (nn == 1 || nn == 2))) acc = fma(-w2[m + 4 * j], D.d[nn + 4 * j], acc);
       }
       lap[m + 4 * nn] = acc;
-    }
-  }
-}
-
-template <int OP>
-__global__ void __launch_bounds__(TT, TSE_MINB) k_tile(Geo G, Dvv D, TileTables tb, TileArgs a) {
-  constexpr TileCfg cfg = tile_cfg(OP);
-  constexpr bool kStage = (OP == OP_STAGE1 || OP == OP_STAGE2 || OP == OP_STAGE3);
-  constexpr int NIN = (OP == OP_STAGE3 || OP == OP_TIME_AVG) ? 2 : 1;
-  constexpr bool kHasOut = cfg.has_out != 0;
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int IN_BYTES = tile_in_bytes(tb.hmax);
-  unsigned char* const outb = smem + NBUF * IN_BYTES;
-  unsigned char* const pp = outb + (kHasOut ? TILE_BYTES : 0);
-  unsigned char* const elb = pp + cfg.npp * PP_BYTES;
-  const int ZERO_OFF = TILE_BYTES + QI * tb.hmax * KC * 8;
-
-  const int t = threadIdx.x;
-  const int g = a.glist ? a.glist[blockIdx.x / NKC] : blockIdx.x / NKC, kc = blockIdx.x % NKC;
-  // warp = EPW elements x 4 levels x QW tracers
-  const int w = t >> 5, lane = t & 31;
-  const int kk = lane & 3, el = EPW * (w % (GE / EPW)) + ((lane >> 2) % EPW), qi = QW * (w / (GE / EPW)) + (lane >> 2) / EPW;
-  const int pl = el * KC + kk;   // plane within one tracer's tile
-  const int p = qi * GPL + pl;   // plane within the QI-tracer tile
-  const int e = g * GE + el, k = kc * KC + kk;
-  const bool evalid = e < G.nelem;
-  const int Q = a.Q;
-  const int hoff = tb.halo_off[g], H = tb.halo_off[g + 1] - hoff;
-
-  // ---- level package -------------------------------------------------------------------------------------------
-  const bool main_pending = (OP == OP_STAGE3) ? (a.pending[1] != 0) : (a.pending[0] != 0);
-  if (t < NBUF) *reinterpret_cast<double*>(smem + t * IN_BYTES + ZERO_OFF) = 0.0;
-  if (cfg.nel > 0 && t < GE * 8) {
-    // element-level fields: thread -> (element t>>3, nodes 2*(t&7), +1)
-    const int pe = t >> 3, c = t & 7, ee = g * GE + pe;
-    double2 e1 = make_double2(0, 0), e2 = e1, rs = e1, t11 = e1, t12 = e1, t22 = e1;
-    if (ee < G.nelem) {
-      const size_t b = (size_t)ee * 16 + 2 * c;
-      const double2 sp = *reinterpret_cast<const double2*>(G.spheremp + b);
-      rs = *reinterpret_cast<const double2*>(G.rspheremp + b);
-      const double2 rm = *reinterpret_cast<const double2*>(G.rmr + b);
-      const double rx0 = main_pending ? rs.x : 1.0, rx1 = main_pending ? rs.y : 1.0;
-      e1 = make_double2(sp.x * rx0, sp.y * rx1);
-      e2 = make_double2(a.dt * (sp.x * rm.x), a.dt * (sp.y * rm.y));
-      if (cfg.T11 >= 0) {
-        const double* T = G.T + (size_t)ee * 48 + 2 * c;
-        t11 = *reinterpret_cast<const double2*>(T);
-        t12 = *reinterpret_cast<const double2*>(T + 16);
-        t22 = *reinterpret_cast<const double2*>(T + 32);
-      }
-    }
-    const int off = (c * GE + pe) * 16;
-    if (cfg.E1 >= 0) *reinterpret_cast<double2*>(elb + cfg.E1 * EL_BYTES + off) = e1;
-    if (cfg.E2 >= 0) *reinterpret_cast<double2*>(elb + cfg.E2 * EL_BYTES + off) = e2;
-    if (cfg.RSPH >= 0) *reinterpret_cast<double2*>(elb + cfg.RSPH * EL_BYTES + off) = rs;
-    if (cfg.T11 >= 0) {
-      *reinterpret_cast<double2*>(elb + cfg.T11 * EL_BYTES + off) = t11;
-      *reinterpret_cast<double2*>(elb + cfg.T12 * EL_BYTES + off) = t12;
-      *reinterpret_cast<double2*>(elb + cfg.T22 * EL_BYTES + off) = t22;
-    }
-  }
-  if (cfg.npp > 0) {
-    // per-plane fields: thread -> (plane t / PARTS, 8 / PARTS consecutive 16-byte chunks)
-    constexpr int PARTS = TT / GPL;
-    const int ppl = t / PARTS, part = t % PARTS;
-    const int pe = g * GE + ppl / KC, pk = kc * KC + ppl % KC;
-    TSE_UNROLL
-    for (int cc = 0; cc < 8 / PARTS; ++cc) {
-      const int c = part * (8 / PARTS) + cc, n = 2 * c;
-      double2 u1 = make_double2(0, 0), u2 = u1, cl = make_double2(1, 1), rd = make_double2(1, 1), rcl = make_double2(1, 1);
-      if (pe < G.nelem) {
-        const size_t lp = lplane(pe, pk) * 16 + n, gb = (size_t)pe * 16 + n;
-        const double2 dpv = *reinterpret_cast<const double2*>(a.dp + lp);
-        const double2 dj = *reinterpret_cast<const double2*>(a.divdp_proj + lp);
-        const double2 rs = *reinterpret_cast<const double2*>(G.rspheremp + gb);
-        const double rx0 = main_pending ? rs.x : 1.0, rx1 = main_pending ? rs.y : 1.0;
-        const double dps0 = dpv.x - a.rhs_mult_dt * dj.x, dps1 = dpv.y - a.rhs_mult_dt * dj.y;
-        const double r0 = 1.0 / dps0, r1 = 1.0 / dps1;
-        rd = make_double2(r0 * rx0, r1 * rx1);
-        if (kStage) {
-          const double2 dd = *reinterpret_cast<const double2*>(a.divdp + lp);
-          const double2 v1 = *reinterpret_cast<const double2*>(a.vn0 + vplane(pe, pk, 0) * 16 + n);
-          const double2 v2 = *reinterpret_cast<const double2*>(a.vn0 + vplane(pe, pk, 1) * 16 + n);
-          const double2 sp = *reinterpret_cast<const double2*>(G.spheremp + gb);
-          const double* mD = G.mD + (size_t)pe * 64 + n;
-          const double2 m11 = *reinterpret_cast<const double2*>(mD), m12 = *reinterpret_cast<const double2*>(mD + 16);
-          const double2 m21 = *reinterpret_cast<const double2*>(mD + 32), m22 = *reinterpret_cast<const double2*>(mD + 48);
-          const double vs10 = v1.x * r0, vs11 = v1.y * r1, vs20 = v2.x * r0, vs21 = v2.y * r1;
-          u1 = make_double2((m11.x * vs10 + m12.x * vs20) * rx0, (m11.y * vs11 + m12.y * vs21) * rx1);
-          u2 = make_double2((m21.x * vs10 + m22.x * vs20) * rx0, (m21.y * vs11 + m22.y * vs21) * rx1);
-          cl = make_double2(sp.x * (dps0 - a.dt * dd.x), sp.y * (dps1 - a.dt * dd.y));
-          rcl = make_double2(1.0 / cl.x, 1.0 / cl.y);
-        }
-      }
-      const int off = (c * GPL + ppl) * 16;
-      if (cfg.U1 >= 0) *reinterpret_cast<double2*>(pp + cfg.U1 * PP_BYTES + off) = u1;
-      if (cfg.U2 >= 0) *reinterpret_cast<double2*>(pp + cfg.U2 * PP_BYTES + off) = u2;
-      if (cfg.CL >= 0) *reinterpret_cast<double2*>(pp + cfg.CL * PP_BYTES + off) = cl;
-      if (cfg.RDP >= 0) *reinterpret_cast<double2*>(pp + cfg.RDP * PP_BYTES + off) = rd;
-      if (cfg.RC >= 0) *reinterpret_cast<double2*>(pp + cfg.RC * PP_BYTES + off) = rcl;
-    }
-  }
-
-  // ---- per-thread DSS gather offsets (bytes inside the IN buffer), two 16-bit offsets per register ----------------
-  unsigned goff[NSLOT / 2];
-  {
-    const int* gs = tb.gsrc_t + (size_t)(evalid ? e : 0) * NSLOT;
-    TSE_UNROLL
-    for (int s = 0; s < NSLOT; ++s) {
-      const int code = evalid ? gs[s] : -1;
-      int off = ZERO_OFF;
-      if (code >= 256) off = TILE_BYTES + ((qi * tb.hmax + (code - 256)) * KC + kk) * 8;
-      else if (code >= 0) {
-        const int p2 = qi * GPL + (code >> 4) * KC + kk, node = code & 15;
-        off = p2 * 128 + ((((node >> 1) ^ swz(p2))) << 4) + (node & 1) * 8;
-      }
-      // IN buffer is < 512 KB / 8: store offsets in units of 8 bytes
-      if (s & 1) goff[s >> 1] |= (unsigned)(off >> 3) << 16;
-      else goff[s >> 1] = (unsigned)(off >> 3);
-    }
-  }
-  auto gofs = [&](int s) -> int { return (int)(((s & 1) ? (goff[s >> 1] >> 16) : (goff[s >> 1] & 0xffffu)) << 3); };
-
-  // ---- halo entries handled by this thread: entry idx -> (h = idx % H, kk2 = idx / H), h fastest for coalescing --------
-  const int nhalo = H * KC;
-  long long hsrc[HPRE];  // double index of the source for tracer 0 (>= 0: in field; < 0: -(index in ghost array) - 1)
-  int hdst[HPRE];        // byte offset in the IN buffer for tracer slot 0
-  TSE_UNROLL
-  for (int r = 0; r < HPRE; ++r) {
-    const int idx = t + r * TT;
-    hsrc[r] = 0;
-    hdst[r] = -1;
-    if (idx < nhalo) {
-      const int h = idx % H, kk2 = idx / H;
-      const int code = tb.halo_src[hoff + h];
-      const int kq = kc * KC + kk2;
-      hdst[r] = TILE_BYTES + (h * KC + kk2) * 8;
-      if (code >= 0) hsrc[r] = (long long)(qplane(code >> 4, 0, kq, Q) * 16 + (code & 15));
-      else hsrc[r] = -((long long)(-code - 2) * Q * NLEV + kq) - 1;
-    }
-  }
-
-  const unsigned smem_u32 = (unsigned)__cvta_generic_to_shared(smem);
-  const int nit = (Q + QI - 1) / QI;
-  const int nitems = nit * NIN;
-  const size_t cta_base = ((size_t)g * NKC + kc) * Q * GPL * 16;  // doubles
-  // own-plane chunk offsets
-  const int own_base = p * 128, own_sw = swz(p);
-  // chunk i = r*TT + t of a tile -> plane r*TT/8 + (t>>3), 16-byte unit t&7
-  auto cp_dst = [&](int r) -> int {
-    const int pi = r * (TT / 8) + (t >> 3);
-    return pi * 128 + (((t & 7) ^ swz(pi)) << 4);
-  };
-  const bool group_full = (g * GE + GE <= G.nelem);
-
-  auto issue = [&](int j) {
-    const int it = j / NIN, which = j % NIN;
-    const double* src = a.src[which];
-    const int q0 = it * QI, nq = min(QI, Q - q0);
-    const double* tsrc = src + cta_base + (size_t)q0 * GPL * 16 + t * 2;
-    const unsigned sb = smem_u32 + (j % NBUF) * IN_BYTES;
-    if (nq == QI) {
-      TSE_UNROLL
-      for (int r = 0; r < 8; ++r) cp_async16(sb + cp_dst(r), tsrc + r * (TT * 2));
-    } else {
-      TSE_UNROLL
-      for (int r = 0; r < 8; ++r)
-        if (r * (TT / 8) + (t >> 3) < nq * GPL) cp_async16(sb + cp_dst(r), tsrc + r * (TT * 2));
-    }
-    if (a.pending[which]) {
-      TSE_UNROLL
-      for (int r = 0; r < HPRE; ++r) {
-        if (hdst[r] >= 0) {
-          for (int qi2 = 0; qi2 < nq; ++qi2) {
-            const double* gp = hsrc[r] >= 0 ? src + hsrc[r] + (size_t)(q0 + qi2) * GPL * 16
-                                            : a.ghost[which] + (-(hsrc[r] + 1)) + (size_t)(q0 + qi2) * NLEV;
-            cp_async8(sb + hdst[r] + qi2 * tb.hmax * KC * 8, gp);
-          }
-        }
-      }
-      for (int idx = t + HPRE * TT; idx < nhalo; idx += TT) {  // groups with more than HPRE*TT/KC halo nodes (irregular patches)
-        const int h = idx % H, kk2 = idx / H;
-        const int code = tb.halo_src[hoff + h];
-        const int kq = kc * KC + kk2;
-        for (int qi2 = 0; qi2 < nq; ++qi2) {
-          const double* gp = (code >= 0) ? src + (qplane(code >> 4, q0 + qi2, kq, Q) * 16 + (code & 15))
-                                         : a.ghost[which] + ((size_t)(-code - 2) * Q + q0 + qi2) * NLEV + kq;
-          cp_async8(sb + TILE_BYTES + ((qi2 * tb.hmax + h) * KC + kk2) * 8, gp);
-        }
-      }
-    }
-    cp_async_commit();
-  };
-
-  // q-invariant per-thread values
-  double sumc = 0.0;
-  __syncthreads();  // package visible
-  if (kStage) {
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    TSE_UNROLL
-    for (int c = 0; c < 8; c += 2) {
-      const double2 x0 = lds128(pp + cfg.CL * PP_BYTES, (c * GPL + pl) * 16);
-      const double2 x1 = lds128(pp + cfg.CL * PP_BYTES, ((c + 1) * GPL + pl) * 16);
-      s0 += x0.x; s1 += x0.y; s2 += x1.x; s3 += x1.y;
-    }
-    sumc = (s0 + s1) + (s2 + s3);
-  }
-  const double cf = (OP == OP_STAGE3) ? a.visc_coef * a.dp0[k] : 0.0;
-
-  double keep[16];  // STAGE3: cf*lap of the first item; TIME_AVG: Qdp(n0)
-  // limiter bounds of this thread's plane, fetched one tracer step of the loop ahead (a global load the math depends on)
-  const size_t pidx0 = (((size_t)g * NKC + kc) * Q + qi) * GPL + pl;
-  double minp_n = 0.0, maxp_n = 0.0;
-  if (kStage && evalid && qi < Q) {
-    minp_n = a.qmin[pidx0];
-    maxp_n = a.qmax[pidx0];
-  }
-  issue(0);
-  if (nitems > 1) issue(1);
-  for (int j = 0; j < nitems; ++j) {
-    if (j + 1 < nitems) cp_async_wait_1(); else cp_async_wait_all();
-    __syncthreads();  // IN[j % NBUF] holds item j; every thread is past the copy-out of the previous item
-    const unsigned char* inb = smem + (j % NBUF) * IN_BYTES;
-    const int it = j / NIN, which = j % NIN;
-    const int q = it * QI + qi;
-    const bool valid = evalid && q < Q;
-    const size_t pidx = (((size_t)g * NKC + kc) * Q + q) * GPL + pl;  // global plane index
-
-    double S[16];
-    TSE_UNROLL
-    for (int c = 0; c < 8; ++c) {
-      const double2 v = lds128(inb, own_base + ((c ^ own_sw) << 4));
-      S[2 * c] = v.x;
-      S[2 * c + 1] = v.y;
-    }
-    if (a.pending[which]) {  // DSS in the reference's unpack order: S, E, N, W edges, then SW, SE, NE, NW corners
-      TSE_UNROLL
-      for (int i = 0; i < 4; ++i) S[i] += lds64(inb, gofs(i));
-      TSE_UNROLL
-      for (int i = 0; i < 4; ++i) S[3 + 4 * i] += lds64(inb, gofs(4 + i));
-      TSE_UNROLL
-      for (int i = 0; i < 4; ++i) S[12 + i] += lds64(inb, gofs(8 + i));
-      TSE_UNROLL
-      for (int i = 0; i < 4; ++i) S[4 * i] += lds64(inb, gofs(12 + i));
-      S[0] += lds64(inb, gofs(16));
-      S[3] += lds64(inb, gofs(17));
-      S[15] += lds64(inb, gofs(18));
-      S[12] += lds64(inb, gofs(19));
-    }
-    __syncthreads();  // all reads of this IN buffer done: refill it with the item after next, overlapping the compute below
-    if (j + NBUF < nitems) issue(j + NBUF);
-
-    const bool last_of_iter = (which == NIN - 1);
-    if (valid) {
-      if (OP == OP_MINMAX || OP == OP_BIHARM_PRE) {
-        TSE_UNROLL
-        for (int c = 0; c < 8; ++c) {
-          const double2 rd = lds128(pp + cfg.RDP * PP_BYTES, (c * GPL + pl) * 16);
-          S[2 * c] *= rd.x;
-          S[2 * c + 1] *= rd.y;
-        }
-        double mn0 = dmin(S[0], S[1]), mx0 = dmax(S[0], S[1]), mn1 = dmin(S[2], S[3]), mx1 = dmax(S[2], S[3]);
-        TSE_UNROLL
-        for (int n = 4; n < 16; n += 4) {
-          mn0 = dmin(mn0, dmin(S[n], S[n + 1]));
-          mx0 = dmax(mx0, dmax(S[n], S[n + 1]));
-          mn1 = dmin(mn1, dmin(S[n + 2], S[n + 3]));
-          mx1 = dmax(mx1, dmax(S[n + 2], S[n + 3]));
-        }
-        a.qmin_loc[pidx] = dmin(mn0, mn1);
-        a.qmax_loc[pidx] = dmax(mx0, mx1);
-        if (OP == OP_BIHARM_PRE) {
-          double lap[16];
-          laplace_wk_el(S, D, elb + cfg.T11 * EL_BYTES, elb + cfg.T12 * EL_BYTES, elb + cfg.T22 * EL_BYTES, el, lap);
-          TSE_UNROLL
-          for (int n = 0; n < 16; ++n) S[n] = lap[n];
-        }
-      } else if (OP == OP_RESOLVE) {
-        TSE_UNROLL
-        for (int c = 0; c < 8; ++c) {
-          const double2 rs = lds128(elb + cfg.RSPH * EL_BYTES, (c * GE + el) * 16);
-          S[2 * c] *= rs.x;
-          S[2 * c + 1] *= rs.y;
-        }
-      } else if (OP == OP_TIME_AVG) {
-        if (which == 0) {
-          TSE_UNROLL
-          for (int n = 0; n < 16; ++n) keep[n] = S[n];
-        } else {
-          TSE_UNROLL
-          for (int c = 0; c < 8; ++c) {
-            double2 rs = lds128(elb + cfg.RSPH * EL_BYTES, (c * GE + el) * 16);
-            if (!a.pending[1]) rs = make_double2(1.0, 1.0);
-            S[2 * c] = (keep[2 * c] + (a.rkstage - 1.0) * (rs.x * S[2 * c])) / a.rkstage;
-            S[2 * c + 1] = (keep[2 * c + 1] + (a.rkstage - 1.0) * (rs.y * S[2 * c + 1])) / a.rkstage;
-          }
-        }
-      } else if (OP == OP_STAGE3 && which == 0) {
-        // second half of biharmonic_wk_scalar_minmax: lap(rspheremp*DSS(qtens)); Qtens_biharmonic*spheremp = cf*lap
-        TSE_UNROLL
-        for (int c = 0; c < 8; ++c) {
-          const double2 rs = lds128(elb + cfg.RSPH * EL_BYTES, (c * GE + el) * 16);
-          S[2 * c] *= rs.x;
-          S[2 * c + 1] *= rs.y;
-        }
-        double lap[16];
-        laplace_wk_el(S, D, elb + cfg.T11 * EL_BYTES, elb + cfg.T12 * EL_BYTES, elb + cfg.T22 * EL_BYTES, el, lap);
-        TSE_UNROLL
-        for (int n = 0; n < 16; ++n) keep[n] = cf * lap[n];
-      } else if (kStage) {
-        double minp = minp_n, maxp = maxp_n;
-        if (evalid && q + QI < Q) {
-          minp_n = a.qmin[pidx + (size_t)QI * GPL];
-          maxp_n = a.qmax[pidx + (size_t)QI * GPL];
-        }
-        if (OP == OP_STAGE2) {
-          double mn0 = 1e300, mx0 = -1e300, mn1 = 1e300, mx1 = -1e300;
-          TSE_UNROLL
-          for (int c = 0; c < 8; ++c) {
-            const double2 rd = lds128(pp + cfg.RDP * PP_BYTES, (c * GPL + pl) * 16);
-            const double q0v = S[2 * c] * rd.x, q1v = S[2 * c + 1] * rd.y;
-            mn0 = dmin(mn0, q0v);
-            mx0 = dmax(mx0, q0v);
-            mn1 = dmin(mn1, q1v);
-            mx1 = dmax(mx1, q1v);
-          }
-          minp = dmin(minp, dmin(mn0, mn1));
-          maxp = dmax(maxp, dmax(mx0, mx1));
-        }
-        double y[16];
-        asm volatile("" ::: "memory");
-#ifdef TSE_SKIP_DIV
-        TSE_UNROLL
-        for (int n = 0; n < 16; ++n) y[n] = S[n];
-#else
-        flux_div(S, pp + cfg.U1 * PP_BYTES, pp + cfg.U2 * PP_BYTES, pl, D, y);
-#endif
-        asm volatile("" ::: "memory");
-        const unsigned e1a = smem_u32 + (unsigned)(elb - smem) + (cfg.E1 < 0 ? 0 : cfg.E1) * EL_BYTES + el * 16;
-        const unsigned e2a = smem_u32 + (unsigned)(elb - smem) + (cfg.E2 < 0 ? 0 : cfg.E2) * EL_BYTES + el * 16;
-        TSE_UNROLL
-        for (int c = 0; c < 8; ++c) {
-          const double2 e1 = lds128v(e1a + c * GE * 16);
-          const double2 e2 = lds128v(e2a + c * GE * 16);
-          y[2 * c] = fma(-e2.x, y[2 * c], e1.x * S[2 * c]);
-          y[2 * c + 1] = fma(-e2.y, y[2 * c + 1], e1.y * S[2 * c + 1]);
-          if (OP == OP_STAGE3) {
-            y[2 * c] += keep[2 * c];
-            y[2 * c + 1] += keep[2 * c + 1];
-          }
-        }
-        asm volatile("" ::: "memory");
-#ifndef TSE_SKIP_LIMITER
-        limiter_y(y, smem_u32 + (unsigned)(pp - smem) + (cfg.CL < 0 ? 0 : cfg.CL) * PP_BYTES + pl * 16,
-                  smem_u32 + (unsigned)(pp - smem) + (cfg.RC < 0 ? 0 : cfg.RC) * PP_BYTES + pl * 16, sumc, minp, maxp);
-#endif
-        asm volatile("" ::: "memory");
-        a.qmin[pidx] = minp;
-        a.qmax[pidx] = maxp;
-        TSE_UNROLL
-        for (int n = 0; n < 16; ++n) S[n] = y[n];
-      }
-    }
-
-    if (kHasOut && last_of_iter) {
-      if (valid) {
-        TSE_UNROLL
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<double2*>(outb + own_base + ((c ^ own_sw) << 4)) = make_double2(S[2 * c], S[2 * c + 1]);
-      }
-      __syncthreads();
-      const int q0 = it * QI, nq = min(QI, Q - q0);
-      double* tdst = a.out + cta_base + (size_t)q0 * GPL * 16 + t * 2;
-      if (nq == QI && group_full) {
-        TSE_UNROLL
-        for (int r = 0; r < 8; ++r) *reinterpret_cast<double2*>(tdst + r * (TT * 2)) = lds128(outb, cp_dst(r));
-      } else {
-        TSE_UNROLL
-        for (int r = 0; r < 8; ++r) {
-          const int pi = r * (TT / 8) + (t >> 3);
-          if (pi < nq * GPL && g * GE + ((pi / KC) % GE) < G.nelem)
-            *reinterpret_cast<double2*>(tdst + r * (TT * 2)) = lds128(outb, cp_dst(r));
-        }
-      }
     }
   }
 }
