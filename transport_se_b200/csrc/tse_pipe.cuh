@@ -70,6 +70,24 @@ __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
       "r"(parity)
       : "memory");
 }
+// same, for waits that are expected to be long (the producer waiting for a stage to drain): back off between polls so that
+// the spinning warp does not take issue slots from the math warps of its scheduler
+__device__ __forceinline__ void mbar_wait_backoff(unsigned addr, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "LAB_WAIT:\n"
+      "nanosleep.u32 64;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
 // completion of all cp.async issued so far by this thread counts as one (pre-counted) arrival on the mbarrier
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(unsigned addr) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(addr) : "memory");
@@ -90,7 +108,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;\n" ::"n"(TT) : "memory"); }
 
 template <int OP>
-__global__ void __launch_bounds__(PT, TSE_MINB) k_pipe(const __grid_constant__ PipeMaps maps, Geo G, Dvv D, TileTables tb, TileArgs a) {
+__global__ void __launch_bounds__(PT, (PT > 256 ? 1 : TSE_MINB)) k_pipe(const __grid_constant__ PipeMaps maps, Geo G, Dvv D, TileTables tb, TileArgs a) {
   constexpr TileCfg cfg = tile_cfg(OP);
   constexpr bool kStage = (OP == OP_STAGE1 || OP == OP_STAGE2 || OP == OP_STAGE3);
   constexpr int NIN = (OP == OP_STAGE3 || OP == OP_TIME_AVG) ? 2 : 1;
@@ -147,7 +165,7 @@ __global__ void __launch_bounds__(PT, TSE_MINB) k_pipe(const __grid_constant__ P
     for (int j = 0; j < nitems; ++j) {
       const int b = j % NST, it = j / NIN, which = j % NIN;
       const int q0 = it * QI, nq = min(QI, Q - q0);
-      if (j >= NST) mbar_wait(empty_bar(b), (unsigned)(((j / NST) - 1) & 1));
+      if (j >= NST) mbar_wait_backoff(empty_bar(b), (unsigned)(((j / NST) - 1) & 1));
       const unsigned sb = smem_u32 + b * IN_STRIDE;
       if (lane == 0) {
         mbar_arrive_expect_tx(full_bar(b), (unsigned)(nq * GPL * 128));
@@ -210,12 +228,10 @@ __global__ void __launch_bounds__(PT, TSE_MINB) k_pipe(const __grid_constant__ P
     }
   }
   if (cfg.npp > 0) {
-    constexpr int PARTS = TT / GPL;
-    const int ppl = t / PARTS, part = t % PARTS;
-    const int pe = g * GE + ppl / KC, pk = kc * KC + ppl % KC;
-    TSE_UNROLL
-    for (int cc = 0; cc < 8 / PARTS; ++cc) {
-      const int c = part * (8 / PARTS) + cc, n = 2 * c;
+    // (plane, 16-byte chunk) pairs of the GPL x 8 chunks, strided over the consumer threads
+    for (int i = t; i < GPL * 8; i += TT) {
+      const int ppl = i >> 3, c = i & 7, n = 2 * c;
+      const int pe = g * GE + ppl / KC, pk = kc * KC + ppl % KC;
       double2 u1 = make_double2(0, 0), u2 = u1, cl = make_double2(1, 1), rd = make_double2(1, 1), rcl = make_double2(1, 1);
       if (pe < G.nelem) {
         const size_t lp = lplane(pe, pk) * 16 + n, gb = (size_t)pe * 16 + n;
@@ -297,7 +313,7 @@ __global__ void __launch_bounds__(PT, TSE_MINB) k_pipe(const __grid_constant__ P
   }
   for (int j = 0; j < nitems; ++j) {
     const int b = j % NST;
-    mbar_wait(full_bar(b), (unsigned)((j / NST) & 1));
+    mbar_wait_backoff(full_bar(b), (unsigned)((j / NST) & 1));
     const unsigned char* inb = smem + b * IN_STRIDE;
     const int it = j / NIN, which = j % NIN;
     const int q = it * QI + qi;

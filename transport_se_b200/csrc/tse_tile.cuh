@@ -32,9 +32,12 @@ namespace tse {
 constexpr int QI = TSE_QI;             // tracers per pipeline step
 constexpr int TT = QI * GPL;           // threads per CTA (256 for QI = 4)
 constexpr int TILE_BYTES = TT * 128;   // 32 KB for QI = 4
-constexpr int QW = QI < 8 ? QI : 8;    // tracers per warp
+#ifndef TSE_QW
+#define TSE_QW (TSE_QI < 8 ? ((TSE_QI % 2) ? TSE_QI : 2) : 8)
+#endif
+constexpr int QW = TSE_QW;             // tracers per warp (2: a warp is 4 elements x 4 levels x 2 tracers)
 constexpr int EPW = 8 / QW;            // elements per warp (1 for QI >= 8: the limiter's work is a property of the element)
-static_assert(KC == 4 && (QI % QW) == 0 && (GE % EPW) == 0 && TT % 32 == 0 && TT <= 512, "warp mapping");
+static_assert(KC == 4 && (QI % QW) == 0 && (8 % QW) == 0 && (GE % EPW) == 0 && TT % 32 == 0 && TT <= 512, "warp mapping");
 static_assert(EPW > 1 || (TT / 8) % GPL == 0 || GPL % (TT / 8) == 0, "swizzle");
 
 // XOR swizzle of the 16-byte units of a 128-byte plane: distinct over the 8 planes a quarter-warp reads together
@@ -125,12 +128,41 @@ __device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsig
   }
   if (mass < minp * sumc) minp = mass / sumc;
   if (mass > maxp * sumc) maxp = mass / sumc;
-  bool viol = false;
-  TSE_UNROLL
-  for (int cc = 0; cc < 8; ++cc) {
-    const double2 r = lds128v(rcbase + cc * GPL * 16);
-    const double x0 = y[2 * cc] * r.x, x1 = y[2 * cc + 1] * r.y;
-    viol |= (x0 > maxp) | (x0 < minp) | (x1 > maxp) | (x1 < minp);
+  // any x = y*rc outside [minp, maxp]?  Four predicates OR-accumulate the 32 compares (setp.<cmp>.or), which keeps the
+  // pre-check at DMUL + 2 DSETP per node.
+  unsigned viol;
+  {
+    double x[16];
+    TSE_UNROLL
+    for (int cc = 0; cc < 8; ++cc) {
+      const double2 r = lds128v(rcbase + cc * GPL * 16);
+      x[2 * cc] = y[2 * cc] * r.x;
+      x[2 * cc + 1] = y[2 * cc + 1] * r.y;
+    }
+    asm("{\n"
+        ".reg .pred p0, p1, p2, p3;\n"
+        "setp.gt.f64 p0, %1, %17;\n    setp.lt.or.f64 p0, %1, %18, p0;\n"
+        "setp.gt.f64 p1, %2, %17;\n    setp.lt.or.f64 p1, %2, %18, p1;\n"
+        "setp.gt.f64 p2, %3, %17;\n    setp.lt.or.f64 p2, %3, %18, p2;\n"
+        "setp.gt.f64 p3, %4, %17;\n    setp.lt.or.f64 p3, %4, %18, p3;\n"
+        "setp.gt.or.f64 p0, %5, %17, p0;\n setp.lt.or.f64 p0, %5, %18, p0;\n"
+        "setp.gt.or.f64 p1, %6, %17, p1;\n setp.lt.or.f64 p1, %6, %18, p1;\n"
+        "setp.gt.or.f64 p2, %7, %17, p2;\n setp.lt.or.f64 p2, %7, %18, p2;\n"
+        "setp.gt.or.f64 p3, %8, %17, p3;\n setp.lt.or.f64 p3, %8, %18, p3;\n"
+        "setp.gt.or.f64 p0, %9, %17, p0;\n setp.lt.or.f64 p0, %9, %18, p0;\n"
+        "setp.gt.or.f64 p1, %10, %17, p1;\n setp.lt.or.f64 p1, %10, %18, p1;\n"
+        "setp.gt.or.f64 p2, %11, %17, p2;\n setp.lt.or.f64 p2, %11, %18, p2;\n"
+        "setp.gt.or.f64 p3, %12, %17, p3;\n setp.lt.or.f64 p3, %12, %18, p3;\n"
+        "setp.gt.or.f64 p0, %13, %17, p0;\n setp.lt.or.f64 p0, %13, %18, p0;\n"
+        "setp.gt.or.f64 p1, %14, %17, p1;\n setp.lt.or.f64 p1, %14, %18, p1;\n"
+        "setp.gt.or.f64 p2, %15, %17, p2;\n setp.lt.or.f64 p2, %15, %18, p2;\n"
+        "setp.gt.or.f64 p3, %16, %17, p3;\n setp.lt.or.f64 p3, %16, %18, p3;\n"
+        "or.pred p0, p0, p1;\n or.pred p2, p2, p3;\n or.pred p0, p0, p2;\n"
+        "selp.u32 %0, 1, 0, p0;\n"
+        "}\n"
+        : "=r"(viol)
+        : "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]), "d"(x[4]), "d"(x[5]), "d"(x[6]), "d"(x[7]), "d"(x[8]), "d"(x[9]), "d"(x[10]), "d"(x[11]),
+          "d"(x[12]), "d"(x[13]), "d"(x[14]), "d"(x[15]), "d"(maxp), "d"(minp));
   }
   if (!viol) return;
 
@@ -192,21 +224,26 @@ __device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsig
       for (int cc = 0; cc < 8; cc += 2) {
         const double2 ca = lds128v(cbase + cc * GPL * 16), cb = lds128v(cbase + (cc + 1) * GPL * 16);
         const double cv[4] = {ca.x, ca.y, cb.x, cb.y};
-        TSE_UNROLL
-        for (int u = 0; u < 4; ++u) {
-          const int n = 2 * cc + u;
-          double z = y[n];
-          if (z < bz) z += inc;
-          const double d = z - bz;
-          double ad = 0.0, wd = 0.0;
-          if (d > 0.0) { ad = d; z = bz; }
-          if (d < 0.0) wd = cv[u];
-          y[n] = z;
-          if (u == 0) { a0 = fma(ad, cv[u], a0); w0 += wd; }
-          if (u == 1) { a1 = fma(ad, cv[u], a1); w1 += wd; }
-          if (u == 2) { a2 = fma(ad, cv[u], a2); w2 += wd; }
-          if (u == 3) { a3 = fma(ad, cv[u], a3); w3 += wd; }
-        }
+        // per node: raise if below the bound, then either clip the overshoot (its mass goes to am) or count the node as still
+        // raisable (its weight goes to wsum).  (ptxas turns each conditional FP64 update into op + 2 FSEL, also when the PTX
+        // is written with predicates.)
+#define TSE_SWEEP_NODE(n, cv, acc, wacc) \
+  {                                      \
+    double z = y[n];                     \
+    if (z < bz) z += inc;                \
+    const double d = z - bz;             \
+    if (d > 0.0) {                       \
+      acc = fma(d, cv, acc);             \
+      z = bz;                            \
+    }                                    \
+    if (d < 0.0) wacc += cv;             \
+    y[n] = z;                            \
+  }
+        TSE_SWEEP_NODE(2 * cc + 0, cv[0], a0, w0)
+        TSE_SWEEP_NODE(2 * cc + 1, cv[1], a1, w1)
+        TSE_SWEEP_NODE(2 * cc + 2, cv[2], a2, w2)
+        TSE_SWEEP_NODE(2 * cc + 3, cv[3], a3, w3)
+#undef TSE_SWEEP_NODE
       }
       am = (a0 + a1) + (a2 + a3);
       wsum = (w0 + w1) + (w2 + w3);
