@@ -374,7 +374,7 @@ int dss_level_field(tse_state* s, int DSSopt) {  // the halo of the field (ghost
   if (DSSopt != TSE_DSS_NO_VAR && !f) return fail("tse_euler_step: DSSopt=%d", DSSopt);
   if (!f) return 0;
   if (wait_halo(s)) return 1;
-  k_dss_level<<<level_blocks(s), 128, 0, s->stream>>>(s->geo, *f, s->ghost_lev, s->lev_tmp);
+  k_dss_level<<<(unsigned)((s->ldoubles + 255) / 256), 256, 0, s->stream>>>(s->geo, *f, s->ghost_lev, s->lev_tmp);
   ++s->launches;
   CU(cudaGetLastError());
   std::swap(*f, s->lev_tmp);
