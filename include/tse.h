@@ -114,7 +114,10 @@ int tse_copy_qdp_h2d(tse_handle h, const double* qdp, long long elem_stride, int
 int tse_copy_qdp_d2h(tse_handle h, double* qdp, long long elem_stride, int tl);
 
 /* derived%vn0(np,np,2,nlev), derived%dp(np,np,nlev), derived%eta_dot_dpdn(np,np,nlev+1), derived%omega_p(np,np,nlev);
- * any pointer may be NULL (field left untouched).  Strides in doubles between consecutive elements. */
+ * any pointer may be NULL (field left untouched).  Strides in doubles between consecutive elements.
+ * vn0 and dp are uploaded asynchronously (own stream, second device copy) so that the transfer for step n+1 overlaps the kernels
+ * of step n; device work queued later sees the new values.  From page-locked host memory the copy is still in flight when the
+ * call returns: do not overwrite those buffers before the next blocking entry (tse_synchronize, tse_get_*, tse_diag_*, tse_copy_*). */
 int tse_set_derived(tse_handle h, const double* vn0, long long s_vn0, const double* dp, long long s_dp,
                     const double* eta_dot_dpdn, long long s_eta, const double* omega_p, long long s_omega);
 /* derived%divdp, divdp_proj, eta_dot_dpdn (first nlev levels), omega_p back to the host; NULL = skip */

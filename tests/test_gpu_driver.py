@@ -35,6 +35,11 @@ def test_device_driver_matches_oracle(built, test, qsize):
         err = per_tracer_relerr(got[:, n0 - 1], o.Qdp[:, n0 - 1])
         print("test", test, "cycle", cyc, "relerr", err)
         assert err.max() < 5e-12
+        # global extrema of Q = Qdp/dp (the refresh at the end of prim_run_subcycle, prim_driver_mod.F90:807-822)
+        qmn, qmx = adv.diag_qminmax(n0)
+        rmn, rmx = o.Q.min(axis=(0, 2, 3)), o.Q.max(axis=(0, 2, 3))
+        scale = np.maximum(np.abs(rmx), 1e-300)
+        assert np.max(np.abs(qmx - rmx) / scale) < 5e-12 and np.max(np.abs(qmn - rmn) / scale) < 5e-12
     adv.synchronize()
     # winds of the last tracer step
     vn0, dp = np.zeros_like(o.vn0), np.zeros_like(o.dp)

@@ -89,6 +89,12 @@ struct tse_state {
   double hyai0_ps0 = 0, ps0 = 0;
   double* stage = nullptr;
   size_t stage_doubles = 0;
+  // asynchronous upload of derived%vn0 / derived%dp (tse_set_derived): second copy of both fields, own staging area and stream, so
+  // that the host->device copy of step n+1 runs under the kernels of step n
+  double *vn0_alt = nullptr, *dp_alt = nullptr, *stage_up = nullptr;
+  size_t stage_up_doubles = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_derived = nullptr, ev_alt_free = nullptr;
   int* d_err = nullptr;
   long long launches = 0, stage_launches = 0, dev_bytes = 0;
   std::vector<void*> allocs;
@@ -668,6 +674,20 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
     s->stage_doubles = ne_chunk * per_elem;
     if (dalloc(s, &s->stage, s->stage_doubles)) return 1;
   }
+  {
+    const size_t per_elem = (size_t)16 * NLEV * 2;
+    const size_t ne_chunk = std::max<size_t>(1, std::min<size_t>(ne, ((size_t)16 << 20) / per_elem));
+    s->stage_up_doubles = 2 * ne_chunk * per_elem;  // two halves of 128 MB: the copy of one chunk overlaps the relayout of the previous
+    if (dalloc(s, &s->stage_up, s->stage_up_doubles) || dalloc(s, &s->vn0_alt, 2 * s->ldoubles) || dalloc(s, &s->dp_alt, s->ldoubles)) return 1;
+    {
+      // highest priority: the small relayout kernels must not queue behind the grids of the step that is running
+      int lo = 0, hi = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CU(cudaStreamCreateWithPriority(&s->copy_stream, cudaStreamNonBlocking, hi));
+    }
+    CU(cudaEventCreateWithFlags(&s->ev_derived, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s->ev_alt_free, cudaEventDisableTiming));
+  }
   CU(cudaFuncSetAttribute(k_vertical_remap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RM_SMEM));
   const int hm = s->tiles.hmax;
 #define TSE_TILE_SMEM(OP) CU(cudaFuncSetAttribute(k_pipe<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem_bytes(OP, hm)))
@@ -693,6 +713,12 @@ int tse_finalize(tse_handle s) {
   if (s->ev_boundary) cudaEventDestroy(s->ev_boundary);
   if (s->ev_halo) cudaEventDestroy(s->ev_halo);
   if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+  if (s->copy_stream) {
+    cudaStreamSynchronize(s->copy_stream);
+    cudaStreamDestroy(s->copy_stream);
+  }
+  if (s->ev_derived) cudaEventDestroy(s->ev_derived);
+  if (s->ev_alt_free) cudaEventDestroy(s->ev_alt_free);
   for (cudaEvent_t e : s->event_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : s->marks)
     if (e) cudaEventDestroy(e);
@@ -703,6 +729,7 @@ int tse_finalize(tse_handle s) {
 }
 
 int tse_synchronize(tse_handle s) {
+  if (s->copy_stream) CU(cudaStreamSynchronize(s->copy_stream));
   if (s->comm_stream) CU(cudaStreamSynchronize(s->comm_stream));
   CU(cudaStreamSynchronize(s->stream));
   return check_device_error(s);
@@ -783,10 +810,43 @@ static int level_copy(tse_state* s, double* dev, double* host, long long stride,
   return 0;
 }
 
+// upload of one level field on the copy stream, chunk by chunk through the two halves of stage_up; no host synchronisation
+static int level_upload_async(tse_state* s, double* dev, const double* host, long long stride, int ncomp, int* half) {
+  const size_t per_elem = (size_t)16 * ncomp * NLEV;
+  const size_t half_doubles = s->stage_up_doubles / 2;
+  const size_t ne_chunk = half_doubles / per_elem;
+  for (size_t e0 = 0; e0 < (size_t)s->nelem; e0 += ne_chunk) {
+    const size_t n = std::min(ne_chunk, (size_t)s->nelem - e0);
+    double* st = s->stage_up + (size_t)(*half) * half_doubles;
+    *half ^= 1;
+    if ((size_t)stride == per_elem)  // elements back to back on the host: one linear copy
+      CU(cudaMemcpyAsync(st, host + e0 * per_elem, n * per_elem * 8, cudaMemcpyHostToDevice, s->copy_stream));
+    else
+      CU(cudaMemcpy2DAsync(st, per_elem * 8, host + e0 * (size_t)stride, (size_t)stride * 8, per_elem * 8, n, cudaMemcpyHostToDevice, s->copy_stream));
+    const unsigned blocks = (unsigned)((n * 16 * ncomp * NLEV / 2 + 255) / 256);
+    k_level_relayout<<<blocks, 256, 0, s->copy_stream>>>(dev, st, s->d_h2i + e0, (int)n, ncomp, NLEV, 1);
+    ++s->launches;
+    CU(cudaGetLastError());
+  }
+  return 0;
+}
+
 int tse_set_derived(tse_handle s, const double* vn0, long long s_vn0, const double* dp, long long s_dp, const double* eta, long long s_eta,
                     const double* omega, long long s_omega) {
-  if (level_copy(s, s->vn0, const_cast<double*>(vn0), s_vn0, 2, NLEV, 1)) return 1;
-  if (level_copy(s, s->dp, const_cast<double*>(dp), s_dp, 1, NLEV, 1)) return 1;
+  if (vn0 || dp) {
+    // The new winds go into the second copy of vn0/dp on the copy stream while the kernels queued so far (the previous tracer
+    // step) still read the first; the compute stream picks them up through an event and the two copies swap roles.  The second
+    // copy was last read by the kernels queued before the previous call: ev_alt_free marks their end.
+    CU(cudaStreamWaitEvent(s->copy_stream, s->ev_alt_free, 0));
+    int half = 0;
+    if (vn0 && level_upload_async(s, s->vn0_alt, vn0, s_vn0, 2, &half)) return 1;
+    if (dp && level_upload_async(s, s->dp_alt, dp, s_dp, 1, &half)) return 1;
+    CU(cudaEventRecord(s->ev_derived, s->copy_stream));
+    CU(cudaStreamWaitEvent(s->stream, s->ev_derived, 0));
+    if (vn0) std::swap(s->vn0, s->vn0_alt);
+    if (dp) std::swap(s->dp, s->dp_alt);
+    CU(cudaEventRecord(s->ev_alt_free, s->stream));
+  }
   if (level_copy(s, s->eta_dot, const_cast<double*>(eta), s_eta, 1, NLEV + 1, 1)) return 1;
   if (level_copy(s, s->omega_p, const_cast<double*>(omega), s_omega, 1, NLEV, 1)) return 1;
   return 0;
@@ -959,6 +1019,11 @@ int tse_dcmip_init(tse_handle s, int test_case) {
   if (up(t.zm, &s->dcmip.zm) || up(t.dp_ref, &s->dcmip.dp_ref) || up(t.vm, &s->dcmip.vm) || up(t.vi, &s->dcmip.vi) ||
       up(t.dp_ic, &s->dcmip.dp_ic))
     return 1;
+  {  // ps_v(t=0) = p_i(nlevp) everywhere (dcmip_wrapper_mod.F90:183): what tse_diag_qminmax divides by before the first remap
+    std::vector<double> ps((size_t)s->npad * 16, t.pint[NLEV]);
+    CU(cudaMemcpyAsync(s->ps_v, ps.data(), ps.size() * 8, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+  }
   s->slot_buf[1] = 0; s->slot_buf[2] = 1;
   s->slot_pending[1] = s->slot_pending[2] = 0;
   k_dcmip_ic<<<s->ngroups * NKC, 256, 0, s->stream>>>(test_case, s->nelem, s->Q, s->d_lon, s->d_lat, s->dcmip, s->qbuf[0], s->qbuf[1]);
@@ -1028,7 +1093,36 @@ int tse_diag_mass(tse_handle s, int tl, double* mass) {
   }
   return 0;
 }
-int tse_diag_qminmax(tse_handle, int, double*, double*) { return fail("tse_diag_qminmax: not in this build yet"); }
+int tse_diag_qminmax(tse_handle s, int tl, double* qmin, double* qmax) {
+  if (check_tl(tl) || wait_halo(s)) return 1;
+  const DssView v = view(s, s->slot_buf[tl], s->slot_pending[tl]);
+  const int Q = s->Q;
+  // d_acc doubles as the pair of ordered-integer accumulators: [0,Q) min, [Q,2Q) max
+  unsigned long long* acc = reinterpret_cast<unsigned long long*>(s->d_acc);
+  CU(cudaMemsetAsync(acc, 0xff, sizeof(unsigned long long) * Q, s->stream));
+  CU(cudaMemsetAsync(acc + Q, 0, sizeof(unsigned long long) * Q, s->stream));
+  k_q_minmax<<<plane_grid(s), GPL * QPB, 0, s->stream>>>(s->geo, v, s->d_dA, s->d_dB, s->ps_v, acc, acc + Q);
+  ++s->launches;
+  CU(cudaGetLastError());
+  if (s->comm) {
+    NC(ncclAllReduce(acc, acc, Q, ncclUint64, ncclMin, s->comm, s->stream));
+    NC(ncclAllReduce(acc + Q, acc + Q, Q, ncclUint64, ncclMax, s->comm, s->stream));
+  }
+  std::vector<unsigned long long> h(2 * Q);
+  CU(cudaMemcpyAsync(h.data(), acc, sizeof(unsigned long long) * 2 * Q, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  auto back = [](unsigned long long b) {
+    b = (b >> 63) ? (b & 0x7fffffffffffffffull) : ~b;
+    double x;
+    std::memcpy(&x, &b, 8);
+    return x;
+  };
+  for (int q = 0; q < Q; ++q) {
+    qmin[q] = back(h[q]);
+    qmax[q] = back(h[Q + q]);
+  }
+  return 0;
+}
 
 double tse_timer_ms(tse_handle s, const char* name) {
   resolve_timers(s);

@@ -54,4 +54,41 @@ __global__ void __launch_bounds__(GPL* QPB) k_mass_fixed(Geo G, DssView in, cons
   }
 }
 
+// order-preserving map double -> uint64 (so that atomicMin/atomicMax on the integers order like the doubles)
+__device__ __forceinline__ unsigned long long ordered_bits(double x) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// per-tracer global min/max of Q = Qdp / (dA*ps0 + dB*ps_v)  (the Q refresh of prim_driver_mod.F90:807-822 and the qmin/qmax lines
+// of prim_printstate, prim_state_mod.F90:184-207)
+__global__ void __launch_bounds__(GPL* QPB) k_q_minmax(Geo G, DssView in, const double* __restrict__ dA, const double* __restrict__ dB,
+                                                       const double* __restrict__ ps_v, unsigned long long* __restrict__ omin,
+                                                       unsigned long long* __restrict__ omax) {
+  const ThreadPlane t = thread_plane(G, in.Q);
+  double mn = 1e300, mx = -1e300;
+  if (t.valid) {
+    double v[16];
+    in.load(G, t.e, t.q, t.k, v);
+    const double* ps = ps_v + (size_t)t.e * 16;
+    const double a = dA[t.k], b = dB[t.k];
+    TSE_UNROLL
+    for (int n = 0; n < 16; ++n) {
+      const double q = v[n] / (a + b * ps[n]);
+      mn = dmin(mn, q);
+      mx = dmax(mx, q);
+    }
+  }
+  TSE_UNROLL
+  for (int o = SEG / 2; o > 0; o >>= 1) {
+    mn = dmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = dmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  const int q = blockIdx.y * QPB + threadIdx.x / GPL;
+  if ((threadIdx.x & (SEG - 1)) == 0 && q < in.Q) {
+    atomicMin(omin + q, ordered_bits(mn));
+    atomicMax(omax + q, ordered_bits(mx));
+  }
+}
+
 }  // namespace tse

@@ -1,7 +1,7 @@
 // Tiled tracer-field kernels (sm_100a), warp-specialised: the element operators, limiter, package and tile layout are in
 // tse_tile.cuh; this file is the pipeline around them.
 //
-//   producer warp   moves everything that comes from HBM.  Per pipeline item (QI tracers of one input field) it issues the
+//   producer warps  (2) move everything that comes from HBM.  Per pipeline item (QI tracers of one input field) it issues the
 //                   tile as TMA tensor copies (cp.async.bulk.tensor.2d, 16 planes x 128 B per box, SWIZZLE_128B = the XOR
 //                   swizzle the plane-per-thread reads need) and the DSS halo (68 x KC scattered nodes per tracer for a 4x4
 //                   patch) as 8-byte cp.async; both complete on the stage's "full" mbarrier (complete_tx bytes /
@@ -28,12 +28,17 @@ __host__ __device__ constexpr int pipe_nst(int op) { return (op == OP_BIHARM_PRE
 __host__ __device__ constexpr int pipe_nout(int op) { return (op == OP_TIME_AVG || op == OP_RESOLVE) ? 2 : 1; }
 constexpr int NST_MAX = 4;
 constexpr int NCW = TT / 32;             // consumer warps
-constexpr int PT = TT + 32;              // threads per CTA: consumers + one producer warp
+#ifndef TSE_NPW
+#define TSE_NPW 2
+#endif
+constexpr int NPW = TSE_NPW;             // producer warps: 2 (the 8-byte halo gathers are issue-bound in one warp: 129 -> 124 ms per
+                                         // tracer step at ne120; 4 warps with a setmaxnreg 40/216 register split measured no better)
+constexpr int PT = TT + 32 * NPW;        // threads per CTA: consumers + producer warp(s)
 constexpr int BOX_ROWS = EPW * KC;       // planes per TMA box = one warp's planes of one tracer
 static_assert(BOX_ROWS == 16 && GPL % BOX_ROWS == 0, "TMA box = 16 planes");
 static_assert(EPW > 1, "SWIZZLE_128B is the row&7 XOR");
 
-__host__ __device__ constexpr int pipe_in_stride(int hmax) { return (tile_in_bytes(hmax) + 1023) & ~1023; }
+__host__ __device__ constexpr int pipe_in_stride(int hmax) { return (tile_in_bytes(hmax) + 1023) & ~1023; }  // (stage ops use the bounds area)
 __host__ __device__ constexpr int pipe_smem_bytes(int op, int hmax) {
   return 1024 + pipe_nst(op) * pipe_in_stride(hmax) + (tile_cfg(op).has_out ? pipe_nout(op) * TILE_BYTES : 0) +
          tile_cfg(op).npp * PP_BYTES + tile_cfg(op).nel * EL_BYTES + hmax * KC * 10 + 16 + 2 * NST_MAX * 8;
@@ -99,6 +104,12 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
                "l"(map), "r"(c0), "r"(c1), "r"(mbar)
                : "memory");
 }
+// 1-D bulk copy global -> shared (bytes a multiple of 16), completing on an mbarrier
+__device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(mbar)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, unsigned src) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(map), "r"(c0), "r"(c1), "r"(src)
                : "memory");
@@ -131,6 +142,7 @@ __global__ void __launch_bounds__(PT, (PT > 256 ? 1 : TSE_MINB)) k_pipe(const __
   unsigned short* const hdtab = reinterpret_cast<unsigned short*>(htab + tb.hmax * KC);  // halo destinations (8-byte units)
   const unsigned bar_u32 = (smem_u32 + (unsigned)(reinterpret_cast<unsigned char*>(hdtab + tb.hmax * KC) - smem) + 15u) & ~15u;
   const int ZERO_OFF = TILE_BYTES + QI * tb.hmax * KC * 8;
+  const int BND_OFF = ZERO_OFF + 16;  // limiter bounds of the item: qmin[QI*GPL], qmax[QI*GPL] (stage ops)
   auto full_bar = [&](int b) -> unsigned { return bar_u32 + b * 8; };
   auto empty_bar = [&](int b) -> unsigned { return bar_u32 + (NST + b) * 8; };
 
@@ -149,7 +161,7 @@ __global__ void __launch_bounds__(PT, (PT > 256 ? 1 : TSE_MINB)) k_pipe(const __
 
   if (t == 0) {
     for (int b = 0; b < NST; ++b) {
-      mbar_init(full_bar(b), 1 + 32);  // expect_tx arrive of the issuing lane + one cp.async arrival per producer lane
+      mbar_init(full_bar(b), 1 + 32 * NPW);  // expect_tx arrive of the issuing lane + one cp.async arrival per producer lane
       mbar_init(empty_bar(b), TT);  // every consumer thread releases for itself
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -158,36 +170,38 @@ __global__ void __launch_bounds__(PT, (PT > 256 ? 1 : TSE_MINB)) k_pipe(const __
   fence_proxy_async_smem();
   __syncthreads();
 
-  if (w == NCW) {
+  if (w >= NCW) {
+    const int pw = w - NCW;  // producer warp index: warp 0 issues the tiles, all share the halo
+
     // =============================================== producer warp ===============================================
-    const int hoff = tb.halo_off[g], H = tb.halo_off[g + 1] - hoff;
-    const int nhalo = H * KC;
     const bool any_pending = a.pending[0] || (NIN == 2 && a.pending[1]);
-    if (any_pending) {
-      for (int idx = lane; idx < nhalo; idx += 32) {  // entry idx -> (h = idx % H, kk2 = idx / H), h fastest
-        const int h = idx % H, kk2 = idx / H;
-        const int code = tb.halo_src[hoff + h];
-        const int kq = kc * KC + kk2;
-        htab[idx] = code >= 0 ? (long long)(qplane(code >> 4, 0, kq, Q) * 16 + (code & 15)) : -((long long)(-code - 2) * Q * NLEV + kq) - 1;
-        hdtab[idx] = (unsigned short)((TILE_BYTES + (h * KC + kk2) * 8) >> 3);
-      }
-      __syncwarp();
-    }
-    for (int j = 0; j < nitems; ++j) {
+    auto issue_tile = [&](int j) {  // TMA tile of item j into its stage (after the consumers have drained it)
       const int b = j % NST, it = j / NIN, which = j % NIN;
       const int q0 = it * QI, nq = min(QI, Q - q0);
       if (j >= NST) mbar_wait_backoff(empty_bar(b), (unsigned)(((j / NST) - 1) & 1));
-      const unsigned sb = smem_u32 + b * IN_STRIDE;
-      if (lane == 0) {
-        mbar_arrive_expect_tx(full_bar(b), (unsigned)(nq * GPL * 128));
+      if (lane == 0 && pw == 0) {
+        const unsigned sb = smem_u32 + b * IN_STRIDE;
+        const bool bounds = kStage && which == NIN - 1;  // the item the limiter runs on also brings its bounds (2 x nq*GPL doubles)
+        mbar_arrive_expect_tx(full_bar(b), (unsigned)(nq * GPL * 128 + (bounds ? 2 * nq * GPL * 8 : 0)));
         const CUtensorMap* m = &maps.in[which];
         const int r0 = (int)(row0 + (unsigned)q0 * GPL);
         for (int bx = 0; bx < nq * (GPL / BOX_ROWS); ++bx) tma_load_2d(sb + bx * (BOX_ROWS * 128), m, 0, r0 + bx * BOX_ROWS, full_bar(b));
+        if (bounds) {
+          const size_t off = (size_t)row0 + (size_t)q0 * GPL;  // plane index of (tracer q0, plane 0): bounds are per plane
+          bulk_load(sb + BND_OFF, a.qmin + off, (unsigned)(nq * GPL * 8), full_bar(b));
+          bulk_load(sb + BND_OFF + QI * GPL * 8, a.qmax + off, (unsigned)(nq * GPL * 8), full_bar(b));
+        }
       }
+    };
+    int nhalo = 0;
+    auto issue_halo = [&](int j) {  // DSS halo of item j; every lane then arrives on the stage's full barrier
+      const int b = j % NST, it = j / NIN, which = j % NIN;
+      const int q0 = it * QI, nq = min(QI, Q - q0);
       if (a.pending[which]) {
+        const unsigned sb = smem_u32 + b * IN_STRIDE;
         const double* src = a.src[which];
         const double* ghost = a.ghost[which];
-        for (int idx = lane; idx < nhalo; idx += 32) {
+        for (int idx = lane + 32 * pw; idx < nhalo; idx += 32 * NPW) {
           const long long v = htab[idx];
           const unsigned dst = sb + ((unsigned)hdtab[idx] << 3);
           for (int qi2 = 0; qi2 < nq; ++qi2) {
@@ -197,6 +211,26 @@ __global__ void __launch_bounds__(PT, (PT > 256 ? 1 : TSE_MINB)) k_pipe(const __
         }
       }
       cp_async_mbar_arrive_noinc(full_bar(b));
+    };
+    // the first tiles go out before anything else: they need no table
+    const int nfirst = min(NST, nitems);
+    for (int j = 0; j < nfirst; ++j) issue_tile(j);
+    if (any_pending) {
+      const int hoff = tb.halo_off[g], H = tb.halo_off[g + 1] - hoff;
+      nhalo = H * KC;
+      for (int idx = lane + 32 * pw; idx < nhalo; idx += 32 * NPW) {  // entry idx -> (h = idx % H, kk2 = idx / H), h fastest
+        const int h = idx % H, kk2 = idx / H;
+        const int code = tb.halo_src[hoff + h];
+        const int kq = kc * KC + kk2;
+        htab[idx] = code >= 0 ? (long long)(qplane(code >> 4, 0, kq, Q) * 16 + (code & 15)) : -((long long)(-code - 2) * Q * NLEV + kq) - 1;
+        hdtab[idx] = (unsigned short)((TILE_BYTES + (h * KC + kk2) * 8) >> 3);
+      }
+      if (NPW > 1) asm volatile("bar.sync 2, %0;\n" ::"n"(32 * NPW) : "memory"); else __syncwarp();
+    }
+    for (int j = 0; j < nfirst; ++j) issue_halo(j);
+    for (int j = nfirst; j < nitems; ++j) {
+      issue_tile(j);
+      issue_halo(j);
     }
     return;
   }
@@ -207,6 +241,17 @@ __global__ void __launch_bounds__(PT, (PT > 256 ? 1 : TSE_MINB)) k_pipe(const __
   const int p = qi * GPL + pl;   // plane within the QI-tracer tile
   const int e = g * GE + el, k = kc * KC + kk;
   const bool evalid = e < G.nelem;
+
+  // the DSS gather table of this thread's element: loaded first so that its latency overlaps the package loads
+  int gsv[NSLOT];
+  {
+    const int4* gs4 = reinterpret_cast<const int4*>(tb.gsrc_t + (size_t)(evalid ? e : 0) * NSLOT);
+    TSE_UNROLL
+    for (int s4 = 0; s4 < NSLOT / 4; ++s4) {
+      const int4 v = gs4[s4];
+      gsv[4 * s4] = v.x; gsv[4 * s4 + 1] = v.y; gsv[4 * s4 + 2] = v.z; gsv[4 * s4 + 3] = v.w;
+    }
+  }
 
   // ---- level package (see tse_tile.cuh) ------------------------------------------------------------------------------
   const bool main_pending = (OP == OP_STAGE3) ? (a.pending[1] != 0) : (a.pending[0] != 0);
@@ -240,7 +285,11 @@ __global__ void __launch_bounds__(PT, (PT > 256 ? 1 : TSE_MINB)) k_pipe(const __
   }
   if (cfg.npp > 0) {
     // (plane, 16-byte chunk) pairs of the GPL x 8 chunks, strided over the consumer threads
-    for (int i = t; i < GPL * 8; i += TT) {
+    constexpr int NPK = (GPL * 8 + TT - 1) / TT;
+    TSE_UNROLL
+    for (int r = 0; r < NPK; ++r) {
+      const int i = t + r * TT;
+      if (GPL * 8 % TT != 0 && i >= GPL * 8) break;
       const int ppl = i >> 3, c = i & 7, n = 2 * c;
       const int pe = g * GE + ppl / KC, pk = kc * KC + ppl % KC;
       double2 u1 = make_double2(0, 0), u2 = u1, cl = make_double2(1, 1), rd = make_double2(1, 1), rcl = make_double2(1, 1);
@@ -280,10 +329,9 @@ __global__ void __launch_bounds__(PT, (PT > 256 ? 1 : TSE_MINB)) k_pipe(const __
   // ---- per-thread DSS gather offsets (bytes inside an IN stage), two 16-bit offsets (8-byte units) per register ---------
   unsigned goff[NSLOT / 2];
   {
-    const int* gs = tb.gsrc_t + (size_t)(evalid ? e : 0) * NSLOT;
     TSE_UNROLL
     for (int s = 0; s < NSLOT; ++s) {
-      const int code = evalid ? gs[s] : -1;
+      const int code = evalid ? gsv[s] : -1;
       int off = ZERO_OFF;
       if (code >= 256) off = TILE_BYTES + ((qi * tb.hmax + (code - 256)) * KC + kk) * 8;
       else if (code >= 0) {
@@ -316,13 +364,7 @@ __global__ void __launch_bounds__(PT, (PT > 256 ? 1 : TSE_MINB)) k_pipe(const __
   const double rkm1 = a.rkstage - 1.0, rrk = 1.0 / a.rkstage;
 
   double keep[16];  // STAGE3: cf*lap of the first item; TIME_AVG: Qdp(n0)
-  // limiter bounds of this thread's plane, fetched one tracer step of the loop ahead (a global load the math depends on)
   const size_t pidx0 = (((size_t)g * NKC + kc) * Q + qi) * GPL + pl;
-  double minp_n = 0.0, maxp_n = 0.0;
-  if (kStage && evalid && qi < Q) {
-    minp_n = a.qmin[pidx0];
-    maxp_n = a.qmax[pidx0];
-  }
   for (int j = 0; j < nitems; ++j) {
     const int b = j % NST;
     mbar_wait(full_bar(b), (unsigned)((j / NST) & 1));
@@ -353,6 +395,12 @@ __global__ void __launch_bounds__(PT, (PT > 256 ? 1 : TSE_MINB)) k_pipe(const __
       S[15] += lds64(inb, gofs(18));
       S[12] += lds64(inb, gofs(19));
     }
+    // limiter bounds of this plane (brought by the producer with the item: a global load here would sit on the critical path)
+    double minp = 0.0, maxp = 0.0;
+    if (kStage && which == NIN - 1) {
+      minp = lds64(inb, BND_OFF + p * 8);
+      maxp = lds64(inb, BND_OFF + (QI * GPL + p) * 8);
+    }
     {
       // Release the stage as soon as this thread's copies sit in registers.  The arrive must not overtake the loads: an LDS
       // that is still in flight when the producer's refill lands reads the next item (seen on the GPU as rare wrong planes at
@@ -360,6 +408,7 @@ __global__ void __launch_bounds__(PT, (PT > 256 ? 1 : TSE_MINB)) k_pipe(const __
       unsigned dep = 0;
       TSE_UNROLL
       for (int n = 0; n < 16; ++n) dep ^= (unsigned)__double2hiint(S[n]);
+      if (kStage) dep ^= (unsigned)__double2hiint(minp) ^ (unsigned)__double2hiint(maxp);
       mbar_arrive_after(empty_bar(b), dep, (unsigned)a.zero);
     }
 
@@ -422,11 +471,6 @@ __global__ void __launch_bounds__(PT, (PT > 256 ? 1 : TSE_MINB)) k_pipe(const __
         TSE_UNROLL
         for (int n = 0; n < 16; ++n) keep[n] = cf * lap[n];
       } else if (kStage) {
-        double minp = minp_n, maxp = maxp_n;
-        if (q + QI < Q) {
-          minp_n = a.qmin[pidx + (size_t)QI * GPL];
-          maxp_n = a.qmax[pidx + (size_t)QI * GPL];
-        }
         if (OP == OP_STAGE2) {
           double mn0 = 1e300, mx0 = -1e300, mn1 = 1e300, mx1 = -1e300;
           TSE_UNROLL

@@ -84,7 +84,9 @@ __host__ __device__ constexpr TileCfg tile_cfg(int op) {
        : op == OP_BIHARM_PRE ? TileCfg{1, 3, 1, -1, -1, -1, 0, -1, -1, -1, -1, 0, 1, 2}
                              : TileCfg{0, 1, 1, -1, -1, -1, -1, -1, -1, -1, 0, -1, -1, -1};
 }
-__host__ __device__ constexpr int tile_in_bytes(int hmax) { return TILE_BYTES + QI * hmax * KC * 8 + 16; }
+// one IN stage: tile, halo [tracer][halo node][level], a zero (target of absent DSS neighbours), limiter bounds qmin|qmax [tracer][plane]
+constexpr int BND_BYTES = 2 * QI * GPL * 8;
+__host__ __device__ constexpr int tile_in_bytes(int hmax) { return TILE_BYTES + QI * hmax * KC * 8 + 16 + BND_BYTES; }
 
 __device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src));
