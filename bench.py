@@ -207,7 +207,7 @@ def run_ours(args):
         t = torch.tensor([T_ms, stage_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         T_ms, stage_ms = float(t[0]), float(t[1])
-    mass = adv.diag_mass(2 if (nstep % 2 == 0) else 1)
+    mass = adv.diag_mass(1 if (nstep % 2 == 0) else 2)  # the fresh level after TimeLevel_update is n0_qdp (time_mod.F90:85-109)
     # size-independent check at full scale: tracer mass is conserved to roundoff (limiter, DSS, biharmonic and remap all conserve).
     # Only the 4 analytic tracers count: the checkerboard fillers (tracers 5..) start from a field that is discontinuous across
     # element edges, so their mass moves by O(1e-4) in the first DSS projections -- in the oracle by the same amount

@@ -89,3 +89,44 @@ def test_config_errors(built):
         TracerAdvection(m, v, hv, qsize=2, limiter_option=4)      # cuda_mod.F90:513-517 stops too
     with pytest.raises(TseError):
         TracerAdvection(m, v, hv, qsize=2, hypervis_subcycle_q=2)  # namelist_mod.F90:688-692
+
+
+@pytest.mark.parametrize("test,cycles,gold", [
+    (12, 72, dict(L1=0.307665, L2=0.622099, Linf=0.839133, q_max=0.813105, q_min=-9.385639e-06)),    # README:96
+    (11, 864, dict(L1=0.578151, L2=0.865526, Linf=0.883168, q_max=0.187204, q_min=-3.207090e-13)),   # README:94-95
+])
+def test_full_dcmip_run_matches_readme_norms(built, test, cycles, gold):
+    """End-of-run error norms of the complete ne8 DCMIP 1-1 (12 days, 2592 steps) / 1-2 (1 day, 216 steps) runs on the GPU against
+    the numbers the reference publishes for this configuration (72L, rsplit=3, limiter 8, 4 tracers): 5 significant digits
+    (BASELINE.json north_star); tracer mass conserved to roundoff over the whole run."""
+    from transport_se_b200.advection import TracerAdvection
+    from transport_se_b200.diagnostics import dcmip_error_norms
+    ne, qsize = 8, 4
+    m, v, hv, o = make_oracle(ne, qsize, test)   # only for the t=0 mixing ratio and the level heights of the norm formulas
+    tracer = 0 if test == 11 else 1
+    q_i = o.Q[:, tracer].copy()
+    z_mid = o.phi[0, :, 0] / 9.80616
+    adv = TracerAdvection(m, v, hv, qsize=qsize, nu_q=6e16)
+    adv.dcmip_init(test)
+    mass0 = adv.diag_mass(1)
+    nstep = 0
+    for _ in range(cycles):
+        nstep = adv.prim_run_subcycle(TSTEP[ne], nstep)
+    tl = 1 if nstep % 2 == 0 else 2   # TimeLevel_Qdp after the final TimeLevel_update: the fresh level is n0_qdp
+    qdp = np.zeros_like(o.Qdp)
+    adv.copy_qdp_d2h(qdp, tl)
+    ps = np.zeros((o.nelem, 16))
+    adv.get_dp3d_ps(None, ps)
+    # the Q refresh at the end of prim_run_subcycle (prim_driver_mod.F90:807-822): Q = Qdp / (dA*ps0 + dB*ps_v)
+    dA, dB = np.diff(hv["hyai"]) * 1e5, np.diff(hv["hybi"])
+    q_f = qdp[:, tl - 1, tracer] / (dA[None, :, None] + dB[None, :, None] * ps[:, None, :])
+    res = dcmip_error_norms(m, q_i, q_f, z_mid)
+    print("test", test, res)
+    for key in ("L1", "L2", "Linf", "q_max"):
+        assert abs(res[key] - gold[key]) < 5e-6 * max(1.0, abs(gold[key])), (key, res[key], gold[key])
+    assert abs(res["q_min"]) <= 3 * abs(gold["q_min"]) + 1e-12   # roundoff-level, not reproducible between machines (README:80-84)
+    qmn, qmx = adv.diag_qminmax(tl)
+    assert abs(qmx[tracer] - res["q_max"]) < 1e-12 and abs(qmn[tracer] - res["q_min"]) < 1e-12
+    mass1 = adv.diag_mass(tl)
+    assert np.max(np.abs(mass1 - mass0) / mass0) < 1e-12
+    adv.close()

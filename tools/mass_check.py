@@ -14,7 +14,7 @@ tstep = {8: 400.0, 30: 300.0}.get(ne, 75.0 * 120 / ne)
 nstep = 0
 for c in range(cycles):
     nstep = adv.prim_run_subcycle(tstep, nstep)
-    m = adv.diag_mass(2 if nstep % 2 == 0 else 1)
+    m = adv.diag_mass(1 if nstep % 2 == 0 else 2)
     d = np.abs(m - m0) / np.abs(m0)
     print('ne', ne, 'cycle', c, 'max drift %.3e at tracer %d; drift[0:6]' % (d.max(), int(d.argmax())), ' '.join('%.2e' % x for x in d[:6]), 'mass0[0]=%.12f' % m[0], flush=True)
 adv.close()
