@@ -326,7 +326,7 @@ void launch_tile(tse_state* s, TileArgs a, const int* glist = nullptr, int ngl =
   pm.in[0] = map_of(s, a.src[0]);
   pm.in[1] = map_of(s, a.src[1] ? a.src[1] : a.src[0]);
   pm.out = map_of(s, a.out ? a.out : a.src[0]);
-  k_pipe<OP><<<ng * NKC, PT, pipe_smem_bytes(OP, s->tiles.hmax), s->stream>>>(pm, s->geo, s->dvv, s->tiles, a);
+  k_pipe<OP><<<ng * NKC, pipe_threads(OP), pipe_smem_bytes(OP, s->tiles.hmax), s->stream>>>(pm, s->geo, s->dvv, s->tiles, a);
   ++s->launches;
 }
 // producer launch of a field whose boundary nodes are exchanged: boundary groups, then (after `start_comm` queued the pack and

@@ -33,7 +33,9 @@ constexpr int NCW = TT / 32;             // consumer warps
 #endif
 constexpr int NPW = TSE_NPW;             // producer warps: 2 (the 8-byte halo gathers are issue-bound in one warp: 129 -> 124 ms per
                                          // tracer step at ne120; 4 warps with a setmaxnreg 40/216 register split measured no better)
-constexpr int PT = TT + 32 * NPW;        // threads per CTA: consumers + producer warp(s)
+// producer warps / threads per CTA of an op (OP_MINMAX has no halo in the time loop: one producer, and 3 CTAs fit per SM)
+__host__ __device__ constexpr int pipe_npw(int op) { return op == OP_MINMAX ? 1 : NPW; }
+__host__ __device__ constexpr int pipe_threads(int op) { return TT + 32 * pipe_npw(op); }
 constexpr int BOX_ROWS = EPW * KC;       // planes per TMA box = one warp's planes of one tracer
 static_assert(BOX_ROWS == 16 && GPL % BOX_ROWS == 0, "TMA box = 16 planes");
 static_assert(EPW > 1, "SWIZZLE_128B is the row&7 XOR");
@@ -124,12 +126,12 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;\n" ::"n"(TT) : "memory"); }
 
 template <int OP>
-__global__ void __launch_bounds__(PT, (PT > 256 ? 1 : TSE_MINB)) k_pipe(const __grid_constant__ PipeMaps maps, Geo G, Dvv D, TileTables tb, TileArgs a) {
+__global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 : TSE_MINB)) k_pipe(const __grid_constant__ PipeMaps maps, Geo G, Dvv D, TileTables tb, TileArgs a) {
   constexpr TileCfg cfg = tile_cfg(OP);
   constexpr bool kStage = (OP == OP_STAGE1 || OP == OP_STAGE2 || OP == OP_STAGE3);
   constexpr int NIN = (OP == OP_STAGE3 || OP == OP_TIME_AVG) ? 2 : 1;
   constexpr bool kHasOut = cfg.has_out != 0;
-  constexpr int NST = pipe_nst(OP), NOUT = pipe_nout(OP);
+  constexpr int NST = pipe_nst(OP), NOUT = pipe_nout(OP), NPW = pipe_npw(OP);
   extern __shared__ unsigned char smem_raw[];
   const unsigned raw_u32 = (unsigned)__cvta_generic_to_shared(smem_raw);
   unsigned char* const smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);  // SWIZZLE_128B tiles sit on 1 KB boundaries
