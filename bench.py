@@ -41,6 +41,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(ne, qsize, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_euler_stage launch from the committed ncu capture of this configuration
+    (profiles/traffic.json, written by tools/traffic_from_launch_list.py); None if there is no capture for it."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if world != 1 or not os.path.exists(p):
+        return None
+    d = json.load(open(p)).get("ne%d_q%d" % (ne, qsize))
+    return d["k_euler_stage_dram_bytes_per_launch"] if d else None
+
+
 def alg_bytes_per_tracer_step(nelem, qsize, rsplit=3):
     """(13 + 2/rsplit) N_q + 30 N_lev"""
     n_lev = nelem * 16 * 72 * 8
@@ -284,7 +294,7 @@ def run_ours(args):
            "step_hbm": {"alg_bytes_per_tracer_step": alg, "achieved_gbs_per_gpu": alg * n_tracer_steps / T / 1e9 / world, "peak_gbs": peak,
                         "frac": alg * n_tracer_steps / T / 1e9 / world / peak, "frac_of_8TBs": alg * n_tracer_steps / T / 1e9 / world / 8000.0},
            "roofline": {"bound": "hbm", "kernel": "k_euler_stage", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": stage_bytes,
+                        "traffic": measured_traffic(ne, qsize, world), "peak_source": peak_src, "alg_bytes_per_launch": stage_bytes,
                         "avg_launch_ms": stage_avg_s * 1e3, "launches": int(stage_launches),
                         "share_of_step": stage_ms / T_ms},
            "timers_ms": timers, "gpu_launches": int(launches), "clocks": clk, "e2e": e2e,
