@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(256) k_dss_level(Geo G, const double* __restri
   const int g = (int)(gk / NKC), kc = (int)(gk % NKC);
   const int e = g * GE + el, k = kc * KC + kk;
   if (g >= G.ngroups || e >= G.nelem) return;
-  double v = G.spheremp[(size_t)e * 16 + n] * f[i];
+  // products are rounded before they are added (__dmul_rn: no FMA contraction): a neighbour on another GPU arrives as the
+  // already rounded product in the ghost array, and the sum must be bitwise the same either way
+  double v = __dmul_rn(G.spheremp[(size_t)e * 16 + n], f[i]);
   const int* gs = G.gsrc + (size_t)e * NSLOT;
   TSE_UNROLL
   for (int t = 0; t < 3; ++t) {
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(256) k_dss_level(Geo G, const double* __restri
     if (s == -1) continue;
     if (s >= 0) {
       const int es = s >> 4, nd = s & 15;
-      v += G.spheremp[(size_t)es * 16 + nd] * f[lplane(es, k) * 16 + nd];
+      v += __dmul_rn(G.spheremp[(size_t)es * 16 + nd], f[lplane(es, k) * 16 + nd]);
     } else {
       v += ghost[(size_t)(-s - 2) * NLEV + k];
     }
