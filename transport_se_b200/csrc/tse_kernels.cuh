@@ -1,9 +1,9 @@
 // CUDA kernels of the tracer-advection path (sm_100a, FP64): level-field kernels, halo packing, layout conversion and the
-// plane-per-thread view used by the diagnostics.  The tracer-field stage kernels live in tse_tile.cuh.
+// plane-per-thread view used by the diagnostics.  The tracer-field kernels live in tse_pipe.cuh / tse_tile.cuh.
 //
 // The DSS (edgeVpack / bndry_exchangeV / edgeVunpack, edge_mod.F90:366-742) is never materialised as an edge buffer:
 // a kernel that consumes a field produced "pre-DSS" gathers the neighbour nodes in the reference's unpack order while
-// loading (DssView::load here, the shared-memory tile + halo in tse_tile.cuh).
+// loading (DssView::load here, the shared-memory tile + halo in tse_pipe.cuh).
 #pragma once
 #include "tse_ops.cuh"
 

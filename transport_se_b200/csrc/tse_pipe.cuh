@@ -1,12 +1,13 @@
 // Tiled tracer-field kernels (sm_100a), warp-specialised: the element operators, limiter, package and tile layout are in
 // tse_tile.cuh; this file is the pipeline around them.
 //
-//   producer warps  (2) move everything that comes from HBM.  Per pipeline item (QI tracers of one input field) it issues the
-//                   tile as TMA tensor copies (cp.async.bulk.tensor.2d, 16 planes x 128 B per box, SWIZZLE_128B = the XOR
-//                   swizzle the plane-per-thread reads need) and the DSS halo (68 x KC scattered nodes per tracer for a 4x4
-//                   patch) as 8-byte cp.async; both complete on the stage's "full" mbarrier (complete_tx bytes /
-//                   cp.async.mbarrier.arrive.noinc).  It runs up to NST items ahead of the math and never touches registers
-//                   the math needs.
+//   producer warps  (2) move everything that comes from HBM.  Per pipeline item (QI tracers of one input field) one lane issues
+//                   the tile as TMA tensor copies (cp.async.bulk.tensor.2d, 16 planes x 128 B per box, SWIZZLE_128B = the XOR
+//                   swizzle the plane-per-thread reads need) and, for the stage ops, the limiter bounds of the item's planes as
+//                   two 1-D bulk copies; all lanes issue the DSS halo (68 x KC scattered nodes per tracer for a 4x4 patch) as
+//                   8-byte cp.async.  Everything completes on the stage's "full" mbarrier (complete_tx bytes /
+//                   cp.async.mbarrier.arrive.noinc).  The producers run up to NST items ahead of the math and never touch
+//                   registers the math needs.
 //   consumer warps  (TT threads, one 4x4 plane per thread) wait on "full", pull their plane and its DSS neighbours into
 //                   registers, release the stage at once ("empty" mbarrier, one arrive per thread), do the arithmetic, stage
 //                   the result in the OUT tile and hand it to a TMA store (one 2 KB box per tracer per warp, bulk async
@@ -24,9 +25,10 @@ namespace tse {
 // IN stages / OUT buffers per op.  The streaming ops (little math per plane) are bound by bytes in flight: with 2 stages a
 // CTA moves 32 KB per release -> refill round trip (about 2 us), i.e. 4.7 TB/s over the chip; they get 3-4 stages and, where
 // it still leaves 2 CTAs per SM (113 KB each), a double-buffered OUT tile.  The stage ops carry a 40 KB package: 2 + 1.
+// (OP_MINMAX measured slower with 4 stages than with 2.)
 __host__ __device__ constexpr int pipe_nst(int op) { return (op == OP_BIHARM_PRE || op == OP_TIME_AVG || op == OP_RESOLVE) ? 3 : 2; }
 __host__ __device__ constexpr int pipe_nout(int op) { return (op == OP_TIME_AVG || op == OP_RESOLVE) ? 2 : 1; }
-constexpr int NST_MAX = 4;
+constexpr int NST_MAX = 4;               // barrier slots reserved per kind
 constexpr int NCW = TT / 32;             // consumer warps
 #ifndef TSE_NPW
 #define TSE_NPW 2
