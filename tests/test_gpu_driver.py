@@ -92,22 +92,25 @@ def test_config_errors(built):
         TracerAdvection(m, v, hv, qsize=2, hypervis_subcycle_q=2)  # namelist_mod.F90:688-692
 
 
-@pytest.mark.parametrize("test,cycles,gold", [
-    (12, 72, dict(L1=0.307665, L2=0.622099, Linf=0.839133, q_max=0.813105, q_min=-9.385639e-06)),    # README:96
-    (11, 864, dict(L1=0.578151, L2=0.865526, Linf=0.883168, q_max=0.187204, q_min=-3.207090e-13)),   # README:94-95
+@pytest.mark.parametrize("ne,test,cycles,gold", [
+    (8, 12, 72, dict(L1=0.307665, L2=0.622099, Linf=0.839133, q_max=0.813105, q_min=-9.385639e-06)),     # README:96
+    (8, 11, 864, dict(L1=0.578151, L2=0.865526, Linf=0.883168, q_max=0.187204, q_min=-3.207090e-13)),    # README:94-95
+    (30, 12, 96, dict(L1=0.121783, L2=0.361005, Linf=1.092784, q_max=0.836177, q_min=-3.671997e-05)),    # README:129
+    (30, 11, 1152, dict(L1=0.490013, L2=0.789052, Linf=0.918454, q_max=0.445141, q_min=-3.559994e-11)),  # README:127-128
 ])
-def test_full_dcmip_run_matches_readme_norms(built, test, cycles, gold):
-    """End-of-run error norms of the complete ne8 DCMIP 1-1 (12 days, 2592 steps) / 1-2 (1 day, 216 steps) runs on the GPU against
-    the numbers the reference publishes for this configuration (72L, rsplit=3, limiter 8, 4 tracers): 5 significant digits
+def test_full_dcmip_run_matches_readme_norms(built, ne, test, cycles, gold):
+    """End-of-run error norms of the complete DCMIP 1-1 (12 days) / 1-2 (1 day) verification runs at ne8 and ne30 on the GPU against
+    the numbers the reference publishes for these configurations (72L, rsplit=3, limiter 8, 4 tracers): 5 significant digits
     (BASELINE.json north_star); tracer mass conserved to roundoff over the whole run."""
     from transport_se_b200.advection import TracerAdvection
     from transport_se_b200.diagnostics import dcmip_error_norms
-    ne, qsize = 8, 4
+    qsize = 4
     m, v, hv, o = make_oracle(ne, qsize, test)   # only for the t=0 mixing ratio and the level heights of the norm formulas
     tracer = 0 if test == 11 else 1
     q_i = o.Q[:, tracer].copy()
     z_mid = o.phi[0, :, 0] / 9.80616
-    adv = TracerAdvection(m, v, hv, qsize=qsize, nu_q=6e16)
+    from helpers import NU_Q
+    adv = TracerAdvection(m, v, hv, qsize=qsize, nu_q=NU_Q[ne])
     adv.dcmip_init(test)
     mass0 = adv.diag_mass(1)
     nstep = 0
@@ -129,7 +132,9 @@ def test_full_dcmip_run_matches_readme_norms(built, test, cycles, gold):
     qmn, qmx = adv.diag_qminmax(tl)
     assert abs(qmx[tracer] - res["q_max"]) < 1e-12 and abs(qmn[tracer] - res["q_min"]) < 1e-12
     mass1 = adv.diag_mass(tl)
-    assert np.max(np.abs(mass1 - mass0) / mass0) < 1e-12
+    # the tracer the norms are taken on; the checkerboard fillers of 1-2 jump once at the first DSS where a checkerboard line
+    # coincides with an element edge (1.5e-4 at ne30, in the oracle too: tests/test_oracle_golden.py)
+    assert abs(mass1[tracer] - mass0[tracer]) / mass0[tracer] < 1e-12
     adv.close()
 
 
