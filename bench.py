@@ -218,6 +218,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         T_ms, stage_ms = float(t[0]), float(t[1])
     mass = adv.diag_mass(1 if (nstep % 2 == 0) else 2)  # the fresh level after TimeLevel_update is n0_qdp (time_mod.F90:85-109)
+    qmn, qmx = adv.diag_qminmax(1 if (nstep % 2 == 0) else 2)
     # size-independent check at full scale: tracer mass is conserved to roundoff (limiter, DSS, biharmonic and remap all conserve).
     # Only the 4 analytic tracers count: the checkerboard fillers (tracers 5..) start from a field that is discontinuous across
     # element edges, so their mass moves by O(1e-4) in the first DSS projections -- in the oracle by the same amount
@@ -298,7 +299,9 @@ def run_ours(args):
                         "avg_launch_ms": stage_avg_s * 1e3, "launches": int(stage_launches),
                         "share_of_step": stage_ms / T_ms},
            "timers_ms": timers, "gpu_launches": int(launches), "clocks": clk, "e2e": e2e,
-           "tracer_mass": [float(x) for x in mass[:4]], "mass_drift_rel": mass_drift, "mass_drift_rel_checkerboard": mass_drift_fill, "device_bytes": int(adv.device_bytes),
+           "tracer_mass": [float(x) for x in mass[:4]],
+           # order-independent sums and extrema: bitwise equal for any --gpus N when the fields are (compare the lines of a scaling run)
+           "tracer_mass_hex": [float(x).hex() for x in mass[:6]], "tracer_qmin_qmax_hex": [[float(a).hex(), float(b).hex()] for a, b in zip(qmn[:6], qmx[:6])], "mass_drift_rel": mass_drift, "mass_drift_rel_checkerboard": mass_drift_fill, "device_bytes": int(adv.device_bytes),
            "published_context": "reference Fortran/MPI on 960 Edison cores: 42.6 s per model-hour = 39.4 tracer-steps/s (README:174)"}
     if not args.no_cpu and world == 1:
         rate, cores, sample, _ = cpu_oracle_rate(ne, qsize, test, 25.0, 1, 0)
