@@ -144,6 +144,11 @@ int tse_prim_run_subcycle(tse_handle h, double tstep, int* nstep /* in/out tl%ns
 int tse_diag_mass(tse_handle h, int tl, double* mass /* [qsize] */);
 int tse_diag_qminmax(tse_handle h, int tl, double* qmin /* [qsize] */, double* qmax /* [qsize] */);
 
+/* Verification hook (the reference has no counterpart): runs limiter_optim_iter_full (prim_advection_mod.F90:976-1094) exactly as the
+ * stage kernels call it on n independent 4x4 planes.  ptens_w[n][16] in: ptens (tracer mass, the reference's argument); out:
+ * sphweights*ptens_limited (what euler_step stores, :905).  minp/maxp[n] in/out as in the reference.  Needs no handle. */
+int tse_debug_limiter(int n, double* ptens_w, const double* sphweights, const double* dpmass, double* minp, double* maxp);
+
 /* timers: CUDA-event time (ms) accumulated under the reference's GPTL timer names
  * ("prim_advec_tracers_remap_rk2", "euler_step", "vertical_remap", "prim_advance_exp"); returns <0 if unknown */
 double tse_timer_ms(tse_handle h, const char* name);

@@ -47,7 +47,8 @@ EXPORTS = ["tse_last_error", "tse_device_count", "tse_init", "tse_finalize", "ts
            "tse_copy_qdp_h2d", "tse_copy_qdp_d2h", "tse_set_derived", "tse_get_derived", "tse_get_dp3d_ps", "tse_get_qminmax",
            "tse_precompute_divdp", "tse_euler_step", "tse_qdp_time_avg", "tse_vertical_remap", "tse_advec_tracers_remap_rk2",
            "tse_dcmip_init", "tse_prim_run_subcycle", "tse_diag_mass", "tse_diag_qminmax", "tse_timer_ms", "tse_launch_count",
-           "tse_device_bytes", "tse_timer_reset", "tse_mark", "tse_mark_elapsed_ms", "tse_get_wind", "tse_stage_launch_count", "tse_halo_bytes"]
+           "tse_device_bytes", "tse_timer_reset", "tse_mark", "tse_mark_elapsed_ms", "tse_get_wind", "tse_stage_launch_count", "tse_halo_bytes",
+           "tse_debug_limiter"]
 
 
 def cuda_lib():
@@ -96,6 +97,7 @@ def cuda_lib():
         L.tse_get_wind.argtypes = [vp, _dp, ll, _dp, ll]
         L.tse_halo_bytes.argtypes = [vp]
         L.tse_halo_bytes.restype = ll
+        L.tse_debug_limiter.argtypes = [i, _dp, _dp, _dp, _dp, _dp]
         _LIB = L
     return _LIB
 
@@ -257,3 +259,19 @@ class TracerAdvection:
     @property
     def device_bytes(self):
         return self._L.tse_device_bytes(self._h)
+
+
+def debug_limiter(ptens, sphweights, dpmass, minp, maxp):
+    """limiter_optim_iter_full (prim_advection_mod.F90:976-1094) on n independent planes, through the device code the stage
+    kernels use.  ptens/sphweights/dpmass: [n, 16]; minp/maxp: [n].  Returns (sphweights*ptens_limited, minp, maxp)."""
+    L = cuda_lib()
+    y = np.ascontiguousarray(ptens, dtype=np.float64).copy()
+    sw = np.ascontiguousarray(sphweights, dtype=np.float64)
+    dm = np.ascontiguousarray(dpmass, dtype=np.float64)
+    mn = np.ascontiguousarray(minp, dtype=np.float64).copy()
+    mx = np.ascontiguousarray(maxp, dtype=np.float64).copy()
+    n = y.shape[0]
+    assert y.shape == (n, 16) and sw.shape == (n, 16) and dm.shape == (n, 16) and mn.shape == (n,) and mx.shape == (n,)
+    if L.tse_debug_limiter(n, _p(y), _p(sw), _p(dm), _p(mn), _p(mx)):
+        raise TseError(L.tse_last_error().decode())
+    return y, mn, mx

@@ -114,6 +114,7 @@ struct tse_state {
   int *d_glist_b = nullptr, *d_glist_i = nullptr;
   int n_glist_b = 0, n_glist_i = 0;
   bool halo_outstanding = false;
+  bool fused_step = false;  // inside tse_advec_tracers_remap_rk2
   // timers (lazily resolved CUDA events under the reference's GPTL names)
   std::map<std::string, double> timers;
   struct TimerRec { const char* name; cudaEvent_t a, b; };
@@ -305,6 +306,7 @@ TileArgs tile_args(const tse_state* s) {
   a.qmin = s->qmin; a.qmax = s->qmax; a.qmin_loc = s->qmin_loc; a.qmax_loc = s->qmax_loc;
   a.Q = s->Q;
   a.rkstage = 3.0;
+  a.store_bounds = 1;
   return a;
 }
 void set_src(const tse_state* s, TileArgs& a, int i, int buf, int pending) {
@@ -349,7 +351,7 @@ int launch_tile_overlapped(tse_state* s, const TileArgs& a, F start_comm) {
 // neighbor_minmax (viscosity_mod.F90:748-816) after the element extrema of off-GPU neighbours have arrived: 9-way min/max
 int neighbor_minmax(tse_state* s) {
   if (wait_halo(s)) return 1;
-  const size_t total = (size_t)s->ngroups * NKC * s->Q * GPL;
+  const size_t total = (size_t)s->ngroups * NKC * s->Q * GE;
   k_nbr_minmax<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(s->geo, s->Q, s->qmin_loc, s->qmax_loc, s->ghost_mm, s->qmin, s->qmax);
   ++s->launches;
   CU(cudaGetLastError());
@@ -909,6 +911,9 @@ int tse_euler_step(tse_handle s, int np1_qdp, int n0_qdp, double dt, int DSSopt,
   a.rhs_mult_dt = rhs_multiplier * dt;
   a.dt = dt;
   a.visc_coef = -3.0 * dt * s->cfg.nu_q;  // rhs_viss = 3 (prim_advection_mod.F90:797,823)
+  // Stage 2 reads the bounds stage 1 relaxed; stage 3 starts from fresh extrema (:797-806), so what stages 2 and 3 would write
+  // back is never read on the path.  The fused driver skips those stores; the stage-by-stage entry keeps them for tse_get_qminmax.
+  a.store_bounds = (rhs_multiplier == 0 || !s->fused_step) ? 1 : 0;
   int tmp = -1;
   if (wait_halo(s)) return 1;
   if (rhs_multiplier == 0) {
@@ -985,7 +990,8 @@ int tse_vertical_remap(tse_handle s, double dt, int np1, int np1_qdp) {
   a.q = s->qbuf[s->slot_buf[np1_qdp]];
   a.dp = s->dp; a.divdp_proj = s->divdp_proj; a.dp3d = s->dp3d; a.ps_v = s->ps_v;
   a.dA = s->d_dA; a.dB = s->d_dB; a.hyai0_ps0 = s->hyai0_ps0; a.dt = dt; a.Q = s->Q; a.nelem = s->nelem; a.error_flag = s->d_err;
-  k_vertical_remap<<<s->nelem, RM_THREADS, RM_SMEM, s->stream>>>(a);
+  const int rm_threads = std::min(RM_MAX_THREADS, 32 * ((16 * s->Q + 31) / 32));
+  k_vertical_remap<<<s->nelem, rm_threads, RM_SMEM, s->stream>>>(a);
   ++s->launches;
   CU(cudaGetLastError());
   return 0;
@@ -997,9 +1003,11 @@ int tse_advec_tracers_remap_rk2(tse_handle s, double dt, int nstep) {
   const int n0 = ((nstep / qsplit) % 2 == 0) ? 1 : 2, np1 = 3 - n0;
   ScopedTimer tm(s, "prim_advec_tracers_remap_rk2");
   if (tse_precompute_divdp(s)) return 1;
-  if (tse_euler_step(s, np1, n0, dt / 2, TSE_DSS_DIV_VDP_AVE, 0)) return 1;
-  if (tse_euler_step(s, np1, np1, dt / 2, TSE_DSS_ETA, 1)) return 1;
-  if (tse_euler_step(s, np1, np1, dt / 2, TSE_DSS_OMEGA, 2)) return 1;
+  s->fused_step = true;
+  const int rc = tse_euler_step(s, np1, n0, dt / 2, TSE_DSS_DIV_VDP_AVE, 0) || tse_euler_step(s, np1, np1, dt / 2, TSE_DSS_ETA, 1) ||
+                 tse_euler_step(s, np1, np1, dt / 2, TSE_DSS_OMEGA, 2);
+  s->fused_step = false;
+  if (rc) return 1;
   return tse_qdp_time_avg(s, 3, n0, np1);
 }
 
@@ -1026,7 +1034,7 @@ int tse_dcmip_init(tse_handle s, int test_case) {
   }
   s->slot_buf[1] = 0; s->slot_buf[2] = 1;
   s->slot_pending[1] = s->slot_pending[2] = 0;
-  k_dcmip_ic<<<s->ngroups * NKC, 256, 0, s->stream>>>(test_case, s->nelem, s->Q, s->d_lon, s->d_lat, s->dcmip, s->qbuf[0], s->qbuf[1]);
+  k_dcmip_ic<<<s->ngroups * NKC, GE * 16, 0, s->stream>>>(test_case, s->nelem, s->Q, s->d_lon, s->d_lat, s->dcmip, s->qbuf[0], s->qbuf[1]);
   ++s->launches;
   CU(cudaGetLastError());
   return 0;
@@ -1045,7 +1053,7 @@ int tse_prim_run_subcycle(tse_handle s, double tstep, int* nstep_io) {
       ScopedTimer t2(s, "prim_advance_exp");
       // v(n0) was evaluated by the previous step (time 0 for the first one): winds are lagged one step
       const double t_prev = (nstep > 0 ? nstep - 1 : 0) * tstep, t_now = nstep * tstep;
-      k_dcmip_wind<<<s->ngroups * NKC, 256, 0, s->stream>>>(s->test_case, t_prev, t_now, s->nelem, s->d_lon, s->d_lat, s->dcmip, s->vn0,
+      k_dcmip_wind<<<s->ngroups * NKC, GE * 16, 0, s->stream>>>(s->test_case, t_prev, t_now, s->nelem, s->d_lon, s->d_lat, s->dcmip, s->vn0,
                                                             s->dp, s->eta_dot, s->omega_p);
       ++s->launches;
       CU(cudaGetLastError());
@@ -1122,6 +1130,32 @@ int tse_diag_qminmax(tse_handle s, int tl, double* qmin, double* qmax) {
     qmax[q] = back(h[Q + q]);
   }
   return 0;
+}
+
+int tse_debug_limiter(int n, double* ptens_w, const double* sphweights, const double* dpmass, double* minp, double* maxp) {
+  if (n <= 0) return 0;
+  if (!ptens_w || !sphweights || !dpmass || !minp || !maxp) return fail("tse_debug_limiter: null argument");
+  double *d_y = nullptr, *d_s = nullptr, *d_d = nullptr, *d_mn = nullptr, *d_mx = nullptr;
+  const size_t nb = (size_t)n * 16 * 8;
+  int rc = 0;
+  auto ok = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && !rc) rc = fail("tse_debug_limiter: %s: %s", what, cudaGetErrorString(e));
+    return e == cudaSuccess;
+  };
+  if (ok(cudaMalloc(&d_y, nb), "cudaMalloc") && ok(cudaMalloc(&d_s, nb), "cudaMalloc") && ok(cudaMalloc(&d_d, nb), "cudaMalloc") &&
+      ok(cudaMalloc(&d_mn, (size_t)n * 8), "cudaMalloc") && ok(cudaMalloc(&d_mx, (size_t)n * 8), "cudaMalloc") &&
+      ok(cudaMemcpy(d_y, ptens_w, nb, cudaMemcpyHostToDevice), "h2d") && ok(cudaMemcpy(d_s, sphweights, nb, cudaMemcpyHostToDevice), "h2d") &&
+      ok(cudaMemcpy(d_d, dpmass, nb, cudaMemcpyHostToDevice), "h2d") && ok(cudaMemcpy(d_mn, minp, (size_t)n * 8, cudaMemcpyHostToDevice), "h2d") &&
+      ok(cudaMemcpy(d_mx, maxp, (size_t)n * 8, cudaMemcpyHostToDevice), "h2d")) {
+    k_debug_limiter<<<(n + GPL - 1) / GPL, GPL>>>(n, d_y, d_s, d_d, d_mn, d_mx);
+    ok(cudaGetLastError(), "launch");
+    ok(cudaDeviceSynchronize(), "kernel");
+    ok(cudaMemcpy(ptens_w, d_y, nb, cudaMemcpyDeviceToHost), "d2h");
+    ok(cudaMemcpy(minp, d_mn, (size_t)n * 8, cudaMemcpyDeviceToHost), "d2h");
+    ok(cudaMemcpy(maxp, d_mx, (size_t)n * 8, cudaMemcpyDeviceToHost), "d2h");
+  }
+  cudaFree(d_y); cudaFree(d_s); cudaFree(d_d); cudaFree(d_mn); cudaFree(d_mx);
+  return rc;
 }
 
 double tse_timer_ms(tse_handle s, const char* name) {

@@ -29,6 +29,17 @@ namespace tse {
 __host__ __device__ constexpr int pipe_nst(int op) { return (op == OP_BIHARM_PRE || op == OP_TIME_AVG || op == OP_RESOLVE) ? 3 : 2; }
 __host__ __device__ constexpr int pipe_nout(int op) { return (op == OP_TIME_AVG || op == OP_RESOLVE) ? 2 : 1; }
 constexpr int NST_MAX = 4;               // barrier slots reserved per kind
+// Stage release protocol (consumer -> producer, "this stage may be refilled"):
+//   0  fence.proxy.async.shared::cta, then mbarrier.arrive.  The refill is written by the async proxy (TMA, cp.async.bulk);
+//      the consumer's reads are generic-proxy ld.shared.  mbarrier release/acquire orders generic-proxy accesses only, so the
+//      write-after-read across the two proxies needs the proxy fence on the reading side (PTX ISA "async proxy"; the same
+//      fence CUTLASS issues before consumer_release when a TMA load overwrites a buffer read with ld.shared).
+//   1  round-1 protocol: the arrive count is made data-dependent on every loaded register, so the arrive cannot issue before
+//      the loads have returned.  Correct on the hardware, but outside the memory model.
+//   2  plain arrive without fence: WRONG (rare stale planes at ne >= 90 on the B200); kept for the sanitizer runs.
+#ifndef TSE_RELEASE
+#define TSE_RELEASE 0
+#endif
 constexpr int NCW = TT / 32;             // consumer warps
 #ifndef TSE_NPW
 #define TSE_NPW 2
@@ -39,7 +50,7 @@ constexpr int NPW = TSE_NPW;             // producer warps: 2 (the 8-byte halo g
 __host__ __device__ constexpr int pipe_npw(int op) { return op == OP_MINMAX ? 1 : NPW; }
 __host__ __device__ constexpr int pipe_threads(int op) { return TT + 32 * pipe_npw(op); }
 constexpr int BOX_ROWS = EPW * KC;       // planes per TMA box = one warp's planes of one tracer
-static_assert(BOX_ROWS == 16 && GPL % BOX_ROWS == 0, "TMA box = 16 planes");
+static_assert((BOX_ROWS == 8 || BOX_ROWS == 16) && GPL % BOX_ROWS == 0, "TMA box = whole 1 KB swizzle atoms (8 planes)");
 static_assert(EPW > 1, "SWIZZLE_128B is the row&7 XOR");
 
 __host__ __device__ constexpr int pipe_in_stride(int hmax) { return (tile_in_bytes(hmax) + 1023) & ~1023; }  // (stage ops use the bounds area)
@@ -405,16 +416,21 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
       minp = lds64(inb, BND_OFF + p * 8);
       maxp = lds64(inb, BND_OFF + (QI * GPL + p) * 8);
     }
+    // Release the stage as soon as this thread's copies sit in registers (see "Stage release" at the top of this file).
+#if TSE_RELEASE == 0
+    fence_proxy_async_smem();
+    mbar_arrive(empty_bar(b));
+#elif TSE_RELEASE == 1
     {
-      // Release the stage as soon as this thread's copies sit in registers.  The arrive must not overtake the loads: an LDS
-      // that is still in flight when the producer's refill lands reads the next item (seen on the GPU as rare wrong planes at
-      // ne120), so the arrive is made to depend on every loaded register.
       unsigned dep = 0;
       TSE_UNROLL
       for (int n = 0; n < 16; ++n) dep ^= (unsigned)__double2hiint(S[n]);
       if (kStage) dep ^= (unsigned)__double2hiint(minp) ^ (unsigned)__double2hiint(maxp);
       mbar_arrive_after(empty_bar(b), dep, (unsigned)a.zero);
     }
+#else
+    mbar_arrive(empty_bar(b));  // experiments only: unordered against the refill
+#endif
 
     const bool last_of_iter = (which == NIN - 1);
     if (valid) {
@@ -476,18 +492,28 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
         for (int n = 0; n < 16; ++n) keep[n] = cf * lap[n];
       } else if (kStage) {
         if (OP == OP_STAGE2) {
-          double mn0 = 1e300, mx0 = -1e300, mn1 = 1e300, mx1 = -1e300;
+          // qmin = min(qmin, minval(Q)), qmax = max(qmax, maxval(Q)) with Q = rspheremp*DSS/dp (:779-792).  Away from tracer fronts
+          // every Q already lies inside the bounds of stage 1: test that first (2 DSETP per node, no selects) and reduce only
+          // where it fails -- the result is the same either way.
+          double qv[16];
           TSE_UNROLL
           for (int c = 0; c < 8; ++c) {
             const double2 rd = lds128(pp + cfg.RDP * PP_BYTES, (c * GPL + pl) * 16);
-            const double q0v = S[2 * c] * rd.x, q1v = S[2 * c + 1] * rd.y;
-            mn0 = dmin(mn0, q0v);
-            mx0 = dmax(mx0, q0v);
-            mn1 = dmin(mn1, q1v);
-            mx1 = dmax(mx1, q1v);
+            qv[2 * c] = S[2 * c] * rd.x;
+            qv[2 * c + 1] = S[2 * c + 1] * rd.y;
           }
-          minp = dmin(minp, dmin(mn0, mn1));
-          maxp = dmax(maxp, dmax(mx0, mx1));
+          if (any_outside(qv, minp, maxp)) {
+            double mn0 = dmin(qv[0], qv[1]), mx0 = dmax(qv[0], qv[1]), mn1 = dmin(qv[2], qv[3]), mx1 = dmax(qv[2], qv[3]);
+            TSE_UNROLL
+            for (int n = 4; n < 16; n += 4) {
+              mn0 = dmin(mn0, dmin(qv[n], qv[n + 1]));
+              mx0 = dmax(mx0, dmax(qv[n], qv[n + 1]));
+              mn1 = dmin(mn1, dmin(qv[n + 2], qv[n + 3]));
+              mx1 = dmax(mx1, dmax(qv[n + 2], qv[n + 3]));
+            }
+            minp = dmin(minp, dmin(mn0, mn1));
+            maxp = dmax(maxp, dmax(mx0, mx1));
+          }
         }
         double y[16];
         asm volatile("" ::: "memory");
@@ -512,8 +538,10 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
                   smem_u32 + (unsigned)(pp - smem) + (cfg.RC < 0 ? 0 : cfg.RC) * PP_BYTES + pl * 16, sumc, minp, maxp);
 #endif
         asm volatile("" ::: "memory");
-        a.qmin[pidx] = minp;
-        a.qmax[pidx] = maxp;
+        if (a.store_bounds) {  // the relaxed bounds (:1024-1029) are only read again by stage 2 (and by tse_get_qminmax)
+          a.qmin[pidx] = minp;
+          a.qmax[pidx] = maxp;
+        }
         TSE_UNROLL
         for (int n = 0; n < 16; ++n) S[n] = y[n];
       }

@@ -1,39 +1,39 @@
 // vertical_remap + remap_Q_ppm (reference src/share/prim_advection_mod.F90:1242-1330, 98-356), PPM with
 // mirrored boundary cells (vert_remap_q_alg != 2).
 //
-// One CTA per element, 256 threads = 2 tracers in flight x 128 threads.  A thread owns a run of 9 consecutive levels of one
-// column (72 = 8 segments x 9): the PPM stencils (ao(j-2..j+2), dma(j), dma(j+1), ai(j-1), ai(j)) then live in registers as
-// sliding windows, the only neighbour traffic is the two ghost values on either side of the run (shuffles between the 8 lanes
-// that hold a column) and the segment carries of the cumulative mass.  Everything that does not depend on the tracer is set up
-// once per element: source thickness and its reciprocal, the search result (kid, z2) of each target interface (registers), and the
-// PPM grid coefficients of compute_ppm_grids (8 doubles per (column, level), shared memory, read as 4 x 128-bit per level).
-// Shared memory is otherwise only used for what is gathered with a data-dependent index: the parabola coefficients and the
-// cumulative mass of cell kid(k).  Columns are warp-private (a warp holds 4 columns x 8 segments), so the tracer loop needs no
-// CTA barrier; HBM is read and written straight from registers (4 consecutive nodes x 8 levels = 8 sectors per warp request),
-// with the next tracer's run prefetched.
+// One CTA per element; a thread owns one (column, tracer) pair and walks the 72 levels of that column serially, the way the
+// reference's loops do.  Lanes 0..15 of a warp are the 16 columns of one tracer, lanes 16..31 those of the next one, so
+//   * every global access of a warp is two full 128-byte lines (16 nodes x 8 B of one (level, tracer) plane each),
+//   * everything that does not depend on the tracer (reciprocal source thickness, the PPM grid coefficients of
+//     compute_ppm_grids, the search result kid / integration weights of every target interface) is computed once per element
+//     into shared memory as [level][column] and read back as broadcasts: the lanes of the two tracers of a warp read the same
+//     16 addresses, one wavefront per 64-bit and two per 128-bit load, no bank conflicts by construction,
+//   * the PPM stencils (ao(j-2..j), dma(j-2..j-1), ai(j-3..j-2)) live in registers as sliding windows, the cumulative mass is a
+//     running sum in the reference's order, and the parabola of cell j-2 is consumed as soon as it exists by the target cells
+//     whose lower interface lies in it (kid is monotone, so the emission is a merge of two sorted sequences); nothing that
+//     depends on the tracer touches shared memory.
+// The walk reads a ring of 4 levels ahead of the level it emits, and a target cell k is always emitted after source level k+1 has
+// been read (kid(k) >= k-1 by the search rule :159-165), so the remap can run in place.
+// 18 warps per SM (35 tracers x 16 columns) against 8 for the level-parallel version it replaces (which needed 181 KB for
+// per-tracer gather arrays): 40.4 -> see profiles/ for the current number.
 #pragma once
 #include "tse_ops.cuh"
 
 namespace tse {
 
-constexpr int RM_NSEG = 8;                 // segments per column
-constexpr int RM_L = NLEV / RM_NSEG;       // 9 levels per segment
-#ifndef TSE_RM_TQ
-#define TSE_RM_TQ 2
-#endif
-constexpr int RM_TQ = TSE_RM_TQ;           // tracers in flight per CTA
-constexpr int RM_THREADS = RM_TQ * 16 * RM_NSEG;  // 256
-static_assert(RM_L * RM_NSEG == NLEV, "levels split evenly into segments");
-// shared memory (doubles)
-// Bank layout: the 8 lanes of a column sit 9 levels apart.  For 64-bit accesses that is conflict-free when the column stride is
-// 8 mod 16 doubles (72, 88); the 128-bit px reads get a per-(column, segment) copy of their 11 levels, 90 doubles apart.
-constexpr int RM_PXS = 11 * 8 + 2;                // px block of one (column, segment): levels j0..j0+10, 8 doubles each, + pad
-constexpr int RM_LD = 88;                         // column stride of dpo / masso
-constexpr int RS_PX = 0;                          // [16][8][11][8]: px0, px1, px2, px3, px4, px5*(px6-px7), px8, px9
-constexpr int RS_DPO = RS_PX + 16 * RM_NSEG * RM_PXS;  // [16][RM_LD]: dpo(j), j = -1..74 at index j+1
-constexpr int RS_TR = RS_DPO + 16 * RM_LD;        // per tracer in flight: c0,c1,c2 [16][72] (cell j at j-1), masso [16][RM_LD]
-constexpr int RS_TR_SIZE = 16 * (3 * 72 + RM_LD);
-constexpr size_t RM_SMEM = (size_t)(RS_TR + RM_TQ * RS_TR_SIZE) * sizeof(double);
+constexpr int RM_MAX_THREADS = 576;  // 36 tracer slots x 16 columns (35 tracers in one pass); more tracers loop
+constexpr int RM_PF = 4;             // levels read ahead of the PPM stencil (one level chunk)
+// shared memory, in doubles; every array is [index][16 columns]
+constexpr int RS_DPO = 0;                         // [76]: dpo(j), j = -1..74 at index j+1
+constexpr int RS_RDPO = RS_DPO + 76 * 16;         // [72]: 1/dpo(j), j = 1..72 at j-1
+constexpr int RS_PX = RS_RDPO + 72 * 16;          // [75][4] double2, row j = what step j of the walk needs: (px0,px1)(j-1), (px2(j-1), px3(j-2)),
+                                                  // (px4, px5*(px6-px7))(j-2), (px8,px9)(j-2); rows 1..74
+constexpr int RS_PIO = RS_PX + 75 * 4 * 2 * 16;   // [74]: pio(1..74) at index 0..73 (last = sentinel)
+constexpr int RS_PIN = RS_PIO + 74 * 16;          // [73]: pin(1..73)
+constexpr int RS_G = RS_PIN + 73 * 16;            // [72][4]: g1, g2, g3 (integration weights of target interface k+1), dpo(kid(k))
+constexpr int RS_END = RS_G + 72 * 4 * 16;
+constexpr size_t RM_SMEM = (size_t)RS_END * sizeof(double) + 2 * 80 * 16;  // + kid[72][16], cnt[74][16] as bytes (padded to 80 rows)
+static_assert(NLEV == 72 && KC == 4 && RM_PF == KC, "the level walk is unrolled by level chunks");
 
 struct RemapArgs {
   double* q;                 // tracer field of time level np1_qdp (resolved), remapped in place
@@ -50,219 +50,216 @@ struct RemapArgs {
   int* error_flag;           // set to 1 on negative layer thickness (prim_advection_mod.F90:1323)
 };
 
-__global__ void __launch_bounds__(RM_THREADS, 1) k_vertical_remap(RemapArgs a) {
+// stage 1 of compute_ppm (:284-295): limited slope of cell j from ao(j-1), ao(j), ao(j+1) and (px0, px1, px2) of level j
+__device__ __forceinline__ double ppm_dma(double am, double a0, double ap, double2 p01, double p2) {
+  const double dl = a0 - am, dr = ap - a0;
+  const double da = p01.x * (p01.y * dr + p2 * dl);
+  double d = dmin(fabs(da), dmin(2. * fabs(dl), 2. * fabs(dr)));
+  d = copysign(d, da);
+  if (dr * dl <= 0.) d = 0.;
+  return d;
+}
+
+__global__ void __launch_bounds__(RM_MAX_THREADS, 1) k_vertical_remap(RemapArgs a) {
   extern __shared__ double sm[];
   const int e = blockIdx.x;
   if (e >= a.nelem) return;
-  const int t = threadIdx.x;
-
-  // ---- phase A: grids (all 256 threads) ------------------------------------------------------------------------------
+  const int t = threadIdx.x, nthr = blockDim.x;
+  const int n = t & 15;  // column (node of the 4x4 plane)
   double* const s_dpo = sm + RS_DPO;
-  // pio/pin live in the (not yet used) per-tracer area during the set-up
-  double* const s_pio = sm + RS_TR;             // [16][75]: pio(0..73) (73 = sentinel)
-  double* const s_pin = sm + RS_TR + 16 * 75;   // [16][73]: pin(0..72)
+  double* const s_rdpo = sm + RS_RDPO;
+  double2* const s_px = reinterpret_cast<double2*>(sm + RS_PX);
+  double* const s_pio = sm + RS_PIO;
+  double* const s_pin = sm + RS_PIN;
+  double* const s_g = sm + RS_G;
+  unsigned char* const s_kid = reinterpret_cast<unsigned char*>(sm + RS_END);  // [72][16]: kid(k) (1-based cell index)
+  unsigned char* const s_cnt = s_kid + 80 * 16;                                // [74][16]: number of target cells whose kid == j
+
+  // ---- grids: everything below is tracer independent -----------------------------------------------------------------
   bool neg = false;
-  {
-    const int ln = t & 15, lk = t >> 4;  // coalesced mapping: 16 nodes x 16 level lanes
-    for (int k = 1 + lk; k <= NLEV; k += 16) {
-      const size_t lp = lplane(e, k - 1) * 16 + ln;
-      const double d = a.dp[lp] - a.dt * a.divdp_proj[lp];  // dp3d(np1) = dp_star (:1310-1313)
-      a.dp3d[lp] = d;
-      s_dpo[ln * RM_LD + k + 1] = d;
-      neg |= (d < 0.0);
-    }
+  for (int i = t; i < NLEV * 16; i += nthr) {
+    const int k = i >> 4;  // level k+1, column n (i & 15 == n because nthr is a multiple of 16)
+    const size_t lp = lplane(e, k) * 16 + n;
+    const double d = a.dp[lp] - a.dt * a.divdp_proj[lp];  // dp3d(np1) = dp_star (:1310-1313)
+    a.dp3d[lp] = d;
+    s_dpo[(k + 2) * 16 + n] = d;
+    neg |= (d < 0.0);
   }
+  for (int i = t; i < 74 * 16; i += nthr) s_cnt[i] = 0;
   // the reference aborts here (prim_advection_mod.F90:1319-1324); the grid search below needs monotone pressures
   if (__syncthreads_or(neg)) {
     if (t == 0) *a.error_flag = 1;
     return;
   }
-  if (t < 16) {  // sequential sums in the reference's order, one thread per column (once per element)
-    const int n = t;
-    double* dpo = s_dpo + n * RM_LD;
+  if (t < 32) {
+    // sequential sums in the reference's order, one lane per column: lanes 0..15 ps_v and pin, lanes 16..31 pio
     double s = 0.0;
-    for (int k = 1; k <= NLEV; ++k) s += dpo[k + 1];  // sum(dp3d,3)
+#pragma unroll 8
+    for (int k = 1; k <= NLEV; ++k) s += s_dpo[(k + 1) * 16 + n];  // sum(dp3d,3); both half-warps, same value
     const double ps = a.hyai0_ps0 + s;
-    a.ps_v[(size_t)e * 16 + n] = ps;
-    double pin = 0.0, pio = 0.0;
-    s_pin[n * 73] = 0.0;
-    s_pio[n * 75] = 0.0;
-    for (int k = 1; k <= NLEV; ++k) {
-      pin += a.dA[k - 1] + a.dB[k - 1] * ps;  // dp = dA*ps0 + dB*ps_v
-      pio += dpo[k + 1];
-      s_pin[n * 73 + k] = pin;
-      s_pio[n * 75 + k] = pio;
+    if (t < 16) {
+      a.ps_v[(size_t)e * 16 + n] = ps;
+      double pin = 0.0;
+#pragma unroll 4
+      for (int k = 1; k < NLEV; ++k) {
+        pin += a.dA[k - 1] + a.dB[k - 1] * ps;  // dp = dA*ps0 + dB*ps_v (:1314-1316)
+        s_pin[k * 16 + n] = pin;                // pin(k+1) at index k
+      }
+      s_pin[0 * 16 + n] = 0.0;
+      s_pin[NLEV * 16 + n] = s;  // pin(nlev+1) = pio(nlev+1) (:144): the same sequential sum as pio below
+      // mirrored ghost cells (:147-150)
+      s_dpo[0 * 16 + n] = s_dpo[3 * 16 + n];    // dpo(-1) = dpo(2)
+      s_dpo[1 * 16 + n] = s_dpo[2 * 16 + n];    // dpo(0)  = dpo(1)
+      s_dpo[74 * 16 + n] = s_dpo[73 * 16 + n];  // dpo(nlev+1) = dpo(nlev)
+      s_dpo[75 * 16 + n] = s_dpo[72 * 16 + n];  // dpo(nlev+2) = dpo(nlev-1)
+    } else {
+      double pio = 0.0;
+      s_pio[0 * 16 + n] = 0.0;
+#pragma unroll 8
+      for (int k = 1; k <= NLEV; ++k) {
+        pio += s_dpo[(k + 1) * 16 + n];
+        s_pio[k * 16 + n] = pio;  // pio(k+1) at index k
+      }
+      s_pio[(NLEV + 1) * 16 + n] = pio + 1.0;  // sentinel (:141)
     }
-    s_pio[n * 75 + NLEV + 1] = pio + 1.0;  // sentinel (:147)
-    s_pin[n * 73 + NLEV] = pio;            // pin(nlev+1) = pio(nlev+1) (:144)
-    // mirrored ghost cells (:147-150)
-    dpo[0] = dpo[3];    // dpo(-1) = dpo(2)
-    dpo[1] = dpo[2];    // dpo(0)  = dpo(1)
-    dpo[74] = dpo[73];  // dpo(nlev+1) = dpo(nlev)
-    dpo[75] = dpo[72];  // dpo(nlev+2) = dpo(nlev-1)
   }
   __syncthreads();
-  // compute_ppm_grids (:221-260) for every (column, level j = 0..73); dx(j) = dpo[j+1]
-  for (int i = t; i < 16 * RM_NSEG * 11; i += RM_THREADS) {
-    const int n = i / (RM_NSEG * 11), sg = (i / 11) % RM_NSEG, li = i % 11;
-    const int j = RM_L * sg + li;  // levels j0..j0+10 of segment sg (the two runs next to a boundary both hold its levels)
-    const double* dpo = s_dpo + n * RM_LD;
-    const double dm = dpo[j], d0 = dpo[j + 1], d1 = dpo[j + 2];
-    double px[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    px[0] = d0 / (dm + d0 + d1);
-    px[1] = (2. * dm + d0) / (d1 + d0);
-    px[2] = (d0 + 2. * d1) / (dm + d0);
+  // compute_ppm_grids (:221-260) for every (level j = 0..73, column); dx(j) = s_dpo[j+1]
+  for (int i = t; i < 74 * 16; i += nthr) {
+    const int j = i >> 4;
+    const double dm = s_dpo[j * 16 + n], d0 = s_dpo[(j + 1) * 16 + n], d1 = s_dpo[(j + 2) * 16 + n];
+    double px0, px1, px2, px3 = 0, px4 = 0, px5 = 0, px8 = 0, px9 = 0;
+    px0 = d0 / (dm + d0 + d1);
+    px1 = (2. * dm + d0) / (d1 + d0);
+    px2 = (d0 + 2. * d1) / (dm + d0);
     if (j <= NLEV) {
-      const double d2 = dpo[j + 3];
-      px[3] = d0 / (d0 + d1);
-      px[4] = 1. / (dm + d0 + d1 + d2);
+      const double d2 = s_dpo[(j + 3) * 16 + n];
+      px3 = d0 / (d0 + d1);
+      px4 = 1. / (dm + d0 + d1 + d2);
       const double p5 = (2. * d1 * d0) / (d0 + d1), p6 = (dm + d0) / (2. * d0 + d1), p7 = (d2 + d1) / (2. * d1 + d0);
-      px[5] = p5 * (p6 - p7);  // the reference's dx(5)*(dx(6)-dx(7)) (:303), evaluated once
-      px[6] = d0 * (dm + d0) / (2. * d0 + d1);
-      px[7] = d1 * (d1 + d2) / (d0 + 2. * d1);
+      px5 = p5 * (p6 - p7);  // the reference's dx(6)*(dx(7)-dx(8)) (:303), evaluated once
+      px8 = d0 * (dm + d0) / (2. * d0 + d1);
+      px9 = d1 * (d1 + d2) / (d0 + 2. * d1);
     }
-    double2* dst = reinterpret_cast<double2*>(sm + RS_PX + (n * RM_NSEG + sg) * RM_PXS + li * 8);
-    dst[0] = make_double2(px[0], px[1]);
-    dst[1] = make_double2(px[2], px[3]);
-    dst[2] = make_double2(px[4], px[5]);
-    dst[3] = make_double2(px[6], px[7]);
+    // stage-1 coefficients of level j are used by step j+1 (dma(j)), stage-2 coefficients by step j+2 (ai(j))
+    double* r1 = reinterpret_cast<double*>(s_px + (size_t)(j + 1) * 4 * 16 + n);
+    r1[0] = px0; r1[1] = px1;       // pair 0
+    r1[32] = px2;                   // pair 1, first half
+    if (j <= NLEV) {
+      double* r2 = reinterpret_cast<double*>(s_px + (size_t)(j + 2) * 4 * 16 + n);
+      r2[33] = px3;                 // pair 1, second half
+      r2[64] = px4; r2[65] = px5;   // pair 2
+      r2[96] = px8; r2[97] = px9;   // pair 3
+    }
+    if (j >= 1 && j <= NLEV) s_rdpo[(j - 1) * 16 + n] = 1.0 / d0;
   }
-
-  // ---- per-thread, tracer-independent: the run of levels j = j0+1 .. j0+9 of column n ---------------------------------
-  const int half = t / 128;                 // which of the RM_TQ tracers in flight
-  const int tw = t % 128, wv = tw >> 5, lane = tw & 31;
-  const int seg = lane & 7, n = 4 * wv + (lane >> 3);
-  const int j0 = RM_L * seg;
-  const double* dpo = s_dpo + n * RM_LD;
-  int kid[RM_L];
-  double z2[RM_L], rdpo[RM_L];
-  TSE_UNROLL
-  for (int i = 0; i < RM_L; ++i) {
-    const int j = j0 + 1 + i;
-    int kk = j;
-    const double pk = s_pin[n * 73 + j];
-    while (s_pio[n * 75 + kk - 1] <= pk) ++kk;
+  // search (:155-173): kid(k) = old cell holding new interface k+1, z2 its normalised position; integration weights of
+  // integrate_parabola (:349-356) with x1 = -0.5
+  for (int i = t; i < NLEV * 16; i += nthr) {
+    const int k = (i >> 4) + 1;
+    int kk = k;
+    const double pk = s_pin[k * 16 + n];                 // pin(k+1)
+    while (s_pio[(kk - 1) * 16 + n] <= pk) ++kk;         // pio(kk)
     --kk;
     if (kk == NLEV + 1) kk = NLEV;
-    kid[i] = kk;
-    z2[i] = (pk - (s_pio[n * 75 + kk - 1] + s_pio[n * 75 + kk]) * 0.5) / dpo[kk + 1];
-    rdpo[i] = 1.0 / dpo[j + 1];
+    const double dk = s_dpo[(kk + 1) * 16 + n];
+    const double x2 = (pk - (s_pio[(kk - 1) * 16 + n] + s_pio[kk * 16 + n]) * 0.5) / dk, x1 = -0.5;
+    s_kid[(k - 1) * 16 + n] = (unsigned char)kk;
+    double* g = s_g + (size_t)(k - 1) * 4 * 16 + n;
+    g[0] = x2 - x1;
+    g[16] = (x2 * x2 - x1 * x1) * 0.5;
+    g[32] = (x2 * x2 * x2 - x1 * x1 * x1) / 3.0;
+    g[48] = dk;
   }
-  __syncthreads();  // pio/pin are dead: their storage becomes the per-tracer arrays; px is complete
+  __syncthreads();
+  if (t < 16) {  // cells per old cell (kid is monotone: a run-length count per column)
+    for (int k = 0; k < NLEV; ++k) s_cnt[s_kid[k * 16 + n] * 16 + n] += 1;
+  }
+  __syncthreads();
 
-  // ---- phase B: tracers -----------------------------------------------------------------------------------------------
-  double* const s_c0 = sm + RS_TR + half * RS_TR_SIZE + n * 72;
-  double* const s_c1 = s_c0 + 16 * 72;
-  double* const s_c2 = s_c1 + 16 * 72;
-  double* const s_masso = sm + RS_TR + half * RS_TR_SIZE + 3 * 16 * 72 + n * RM_LD;
-  const double2* const s_px = reinterpret_cast<const double2*>(sm + RS_PX + (n * RM_NSEG + seg) * RM_PXS);  // level j0 first
-  const unsigned FULL = 0xffffffffu;  // shuffles run with width 8: the 8 lanes that hold this column
-  size_t goff[RM_L];  // (e, tracer 0, level j-1, node n); consecutive tracers are GPL*16 doubles apart
-  TSE_UNROLL
-  for (int i = 0; i < RM_L; ++i) goff[i] = qplane(e, 0, j0 + i, a.Q) * 16 + n;
-  const double third = 1.0 / 3.0, sixth = 1.0 / 6.0;
-  double nxt[RM_L];
-  TSE_UNROLL
-  for (int i = 0; i < RM_L; ++i) nxt[i] = (half < a.Q) ? a.q[goff[i] + (size_t)half * (GPL * 16)] : 0.0;
-  // both halves run the same number of iterations (warps are not split between halves, but this keeps the loop simple): the
-  // last iteration of the second half is a dry run when Q is odd
-  const int niter = (a.Q + RM_TQ - 1) / RM_TQ;
-  for (int it = 0; it < niter; ++it) {
-    const int q = it * RM_TQ + half;
-    const bool live = q < a.Q;
-    // ao = Qdp/dpo (:187), window w[i+2] = ao(j0+1+i), i = -2..10
-    double w[RM_L + 4], raw[RM_L];
-    TSE_UNROLL
-    for (int i = 0; i < RM_L; ++i) {
-      raw[i] = nxt[i];
-      w[i + 2] = raw[i] * rdpo[i];
-    }
-    if (q + RM_TQ < a.Q) {
-      TSE_UNROLL
-      for (int i = 0; i < RM_L; ++i) nxt[i] = a.q[goff[i] + (size_t)(q + RM_TQ) * (GPL * 16)];
-    }
-    // cumulative mass masso (:184-186): running sum inside the run, segment carries added in segment order (fixed, deterministic)
+  // ---- tracers ---------------------------------------------------------------------------------------------------------
+  const double2* const px = s_px + n;
+  const int skc = a.Q * GPL * 16;  // doubles between consecutive level chunks of one (element, tracer)
+  for (int q = t >> 4; q < a.Q; q += nthr >> 4) {
+    double* const col = a.q + qplane(e, q, 0, a.Q) * 16 + n;  // (level 1, node n) of this tracer
+    // start-up: ao(1), ao(2), the mirrored cells ao(0) = ao(1), ao(-1) = ao(2) (:193-196), dma(0), dma(1), ai(0)
+    double r1 = col[0], r2 = col[16];                           // raw Qdp of cells j-2, j-1 (for the cumulative mass)
+    double ring[RM_PF] = {col[32], col[48], col[skc], col[skc + 16]};  // levels 3..6, read ahead of the stencil
+    double a1 = r1 * s_rdpo[n], a2 = r2 * s_rdpo[16 + n];       // window: a1 = ao(j-2), a2 = ao(j-1) at the top of step j
+    double dma_prev, ai_prev;
     {
-      double run[RM_L];
-      double m = 0.0;
-      TSE_UNROLL
-      for (int i = 0; i < RM_L; ++i) {
-        m += raw[i];
-        run[i] = m;
+      const double2 q01 = px[1 * 64], q2 = px[1 * 64 + 16];     // stage 1 of level 0
+      const double dma0 = ppm_dma(a2, a1, a1, q01, q2.x);
+      const double2 s01 = px[2 * 64], s23 = px[2 * 64 + 16], s45 = px[2 * 64 + 32], s89 = px[2 * 64 + 48];  // stage 1 of level 1, stage 2 of level 0
+      dma_prev = ppm_dma(a1, a1, a2, s01, s23.x);               // dma(1)
+      ai_prev = a1 + s23.y * (a1 - a1) + s45.x * (s45.y * (a1 - a1) - s89.x * dma_prev + s89.y * dma0);  // ai(0) (:300-305)
+    }
+    double masso = 0.0;   // masso(j-2): mass above cell j-2
+    double massn1 = 0.0;
+    int k = 0;            // next target cell (0-based)
+
+    // one step of the walk: newest source value a3 = ao(j) (raw Qdp `raw`), coefficient row `row` = step j
+    auto step = [&](double raw, double a3, const double2* row, int cnt) {
+      const double2 p01 = row[0], p23 = row[16], p45 = row[32], p89 = row[48];
+      // dma(j-1) from ao(j-2), ao(j-1), ao(j) and (px0,px1,px2) of level j-1
+      const double dma = ppm_dma(a1, a2, a3, p01, p23.x);
+      // ai(j-2) (:300-305) with the stage-2 coefficients of level j-2
+      const double ai = a1 + p23.y * (a2 - a1) + p45.x * (p45.y * (a2 - a1) - p89.x * dma + p89.y * dma_prev);
+      // parabola of cell j-2 (:310-333): aj = ao(j-2), al = ai(j-3), ar = ai(j-2)
+      const double aj = a1;
+      double al = ai_prev, ar = ai;
+      if ((ar - aj) * (aj - al) <= 0.) {
+        al = aj;
+        ar = aj;
       }
-      double base = 0.0;
-      TSE_UNROLL
-      for (int s2 = 0; s2 < RM_NSEG - 1; ++s2) {
-        const double tot = __shfl_sync(FULL, m, s2, 8);
-        if (s2 < seg) base += tot;
+      // the reference divides by 6 (:323-329); multiplying by the rounded reciprocal differs by <= 1 ulp
+      if ((ar - al) * (aj - (al + ar) * 0.5) > (ar - al) * (ar - al) * (1.0 / 6.0)) al = 3. * aj - 2. * ar;
+      if ((ar - al) * (aj - (al + ar) * 0.5) < -((ar - al) * (ar - al)) * (1.0 / 6.0)) ar = 3. * aj - 2. * al;
+      const double c0 = 1.5 * aj - (al + ar) * 0.25, c1 = ar - al, c2 = -6. * aj + 3. * (al + ar);
+      // target cells whose lower interface lies in cell j-2: massn2 = masso(kid) + integral*dpo(kid) (:201-209)
+#pragma unroll 1
+      for (; cnt > 0; --cnt) {
+        const double* g = s_g + k * 64 + n;
+        const double integ = c0 * g[0] + c1 * g[16] + c2 * g[32];
+        const double massn2 = masso + integ * g[48];
+        col[(k >> 2) * skc + (k & 3) * 16] = massn2 - massn1;
+        massn1 = massn2;
+        ++k;
       }
-      if (seg == 0) s_masso[0] = 0.0;
-      TSE_UNROLL
-      for (int i = 0; i < RM_L; ++i) s_masso[j0 + 1 + i] = base + run[i];
+      masso += r1;
+      r1 = r2;
+      r2 = raw;
+      a1 = a2;
+      a2 = a3;
+      dma_prev = dma;
+      ai_prev = ai;
+    };
+
+    // steps j = 3 + 4 i + u; source level j sits in chunk (2 + 4 i + u) / 4 at position (2 + u) % 4
+    const double* src = col + skc;  // chunk 1 + i: the ring is refilled from levels j + 4
+#pragma unroll 1
+    for (int i = 0; i < 17; ++i) {
+      const int j = 3 + 4 * i;
+      const double2* row = px + j * 64;
+      const double* rd = s_rdpo + (j - 1) * 16 + n;
+      const unsigned char* cn = s_cnt + (j - 2) * 16 + n;
+      double raw;
+      raw = ring[0]; ring[0] = src[32];        step(raw, raw * rd[0], row, cn[0]);
+      raw = ring[1]; ring[1] = src[48];        step(raw, raw * rd[16], row + 64, cn[16]);
+      raw = ring[2]; if (i < 16) ring[2] = src[skc];      step(raw, raw * rd[32], row + 128, cn[32]);
+      raw = ring[3]; if (i < 16) ring[3] = src[skc + 16]; step(raw, raw * rd[48], row + 192, cn[48]);
+      src += skc;
     }
-    // ghost values from the neighbouring runs; mirrored cells at the column ends (:193-196)
-    {
-      const double up1 = __shfl_up_sync(FULL, w[RM_L + 1], 1, 8), up2 = __shfl_up_sync(FULL, w[RM_L], 1, 8);
-      const double dn1 = __shfl_down_sync(FULL, w[2], 1, 8), dn2 = __shfl_down_sync(FULL, w[3], 1, 8);
-      w[1] = seg == 0 ? w[2] : up1;                               // ao(j0)    | ao(0)  = ao(1)
-      w[0] = seg == 0 ? w[3] : up2;                               // ao(j0-1)  | ao(-1) = ao(2)
-      w[RM_L + 2] = seg == RM_NSEG - 1 ? w[RM_L + 1] : dn1;       // ao(j0+10) | ao(73) = ao(72)
-      w[RM_L + 3] = seg == RM_NSEG - 1 ? w[RM_L] : dn2;           // ao(j0+11) | ao(74) = ao(71)
+    {  // last round, j = 71..74: two real levels, then the mirrored cells ao(73) = ao(72), ao(74) = ao(71)
+      const double2* row = px + 71 * 64;
+      const double* rd = s_rdpo + 70 * 16 + n;
+      const unsigned char* cn = s_cnt + 69 * 16 + n;
+      step(ring[0], ring[0] * rd[0], row, cn[0]);
+      step(ring[1], ring[1] * rd[16], row + 64, cn[16]);
+      const double a71 = a1;                    // at the top of step 73: a1 = ao(71), a2 = ao(72)
+      step(0.0, a2, row + 128, cn[32]);
+      step(0.0, a71, row + 192, cn[48]);
     }
-    // compute_ppm (:267-342) level by level: dma(j), then ai(j-1) (needs dma(j-1), dma(j)), then the parabola of cell j-1
-    double d_prev = 0.0, ai_prev = 0.0;
-    double2 pxa_prev = make_double2(0, 0), pxb_prev = pxa_prev, pxc_prev = pxa_prev;
-    TSE_UNROLL
-    for (int i = -1; i <= RM_L; ++i) {  // level j = j0 + 1 + i (j0 .. j0+10); the window index of ao(j) is i + 2
-      const double2 p01 = s_px[(i + 1) * 4], p23 = s_px[(i + 1) * 4 + 1];
-      const double am = w[i + 1], a0 = w[i + 2], ap = w[i + 3];
-      const double da = p01.x * (p01.y * (ap - a0) + p23.x * (a0 - am));
-      double d = dmin(fabs(da), dmin(2. * fabs(a0 - am), 2. * fabs(ap - a0)));
-      d = copysign(d, da);
-      if ((ap - a0) * (a0 - am) <= 0.) d = 0.;
-      if (i >= 0) {
-        // ai(j-1) with the coefficients of level j-1 (kept from the previous pass); its a0 = ao(j-1) = am, its ap = ao(j) = a0
-        const double ai = am + pxa_prev.y * (a0 - am) + pxb_prev.x * (pxb_prev.y * (a0 - am) - pxc_prev.x * d + pxc_prev.y * d_prev);
-        if (i >= 1) {
-          // parabola of cell j-1 = j0 + i (:310-333): aj = ao(j-1) = am, al = ai(j-2), ar = ai(j-1)
-          const double aj = am;
-          double al = ai_prev, ar = ai;
-          if ((ar - aj) * (aj - al) <= 0.) {
-            al = aj;
-            ar = aj;
-          }
-          // the reference divides by 6 (:323-329); multiplying by the rounded reciprocal differs by <= 1 ulp
-          if ((ar - al) * (aj - (al + ar) * 0.5) > (ar - al) * (ar - al) * sixth) al = 3. * aj - 2. * ar;
-          if ((ar - al) * (aj - (al + ar) * 0.5) < -((ar - al) * (ar - al)) * sixth) ar = 3. * aj - 2. * al;
-          s_c0[j0 + i - 1] = 1.5 * aj - (al + ar) * 0.25;
-          s_c1[j0 + i - 1] = ar - al;
-          s_c2[j0 + i - 1] = -6. * aj + 3. * (al + ar);
-        }
-        ai_prev = ai;
-      }
-      d_prev = d;
-      pxa_prev = p23;                 // (px2, px3)
-      pxb_prev = s_px[(i + 1) * 4 + 2];  // (px4, px5*(px6-px7))
-      pxc_prev = s_px[(i + 1) * 4 + 3];  // (px8, px9)
-    }
-    __syncwarp();
-    // massn2(k) = masso(kid) + integral over the part of cell kid below the new interface (:201-209)
-    double m2[RM_L];
-    TSE_UNROLL
-    for (int i = 0; i < RM_L; ++i) {
-      const int kk = kid[i];
-      const double x1 = -0.5, x2 = z2[i];
-      const double c0 = s_c0[kk - 1], c1 = s_c1[kk - 1], c2 = s_c2[kk - 1];
-      const double integ = c0 * (x2 - x1) + c1 * (x2 * x2 - x1 * x1) * 0.5 + c2 * (x2 * x2 * x2 - x1 * x1 * x1) * third;
-      m2[i] = s_masso[kk - 1] + integ * dpo[kk + 1];
-    }
-    double below = __shfl_up_sync(FULL, m2[RM_L - 1], 1, 8);  // massn2(j0) from the run below
-    if (seg == 0) below = 0.0;
-    if (live) {
-      TSE_UNROLL
-      for (int i = 0; i < RM_L; ++i) a.q[goff[i] + (size_t)q * (GPL * 16)] = m2[i] - (i == 0 ? below : m2[i - 1]);
-    }
-    __syncwarp();  // the next tracer overwrites the column's coefficient / masso arrays
   }
 }
 

@@ -63,6 +63,7 @@ struct TileArgs {
   const double* dp0;
   double *qmin, *qmax, *qmin_loc, *qmax_loc;
   int Q;
+  int store_bounds;  // stage ops: write the limiter's relaxed qmin/qmax back (needed after stage 1; otherwise only for inspection)
   int zero;          // always 0 (a value the compiler cannot fold: see mbar_arrive_after in tse_pipe.cuh)
   const int* glist;  // optional list of groups this launch covers (boundary groups first, interior groups while the halo is in flight)
 };
@@ -102,45 +103,10 @@ __device__ __forceinline__ double2 lds128v(unsigned addr) {
   return v;
 }
 
-// limiter_optim_iter_full (prim_advection_mod.F90:976-1094).  On entry y = c*x (mass contributions, c = sphweights*dpmass);
-// c and rc = 1/c are read from the per-plane package in shared memory (cbase/rcbase = shared address of chunk 0 of this
-// plane, chunk stride GPL*16 bytes).  Sums use 4 interleaved partial accumulators (fixed order, identical on every GPU count).
-//
-// Fast path: mass = sum(y) and the min/max relaxation (:1016-1029) need no x; if no x = y*rc lies outside [minp, maxp] the
-// reference's first sweep finds addmass = 0 and leaves (:1047), so y is returned untouched.
-// Slow path (x in place of y): sweep 1 clips against both bounds.  From then on the direction is fixed: redistributing
-// addmass > 0 raises nodes below maxp, so later sweeps can only find nodes above maxp and addmass stays >= 0 (and the mirror
-// image for addmass < 0); the lower-bound test of the reference's sweeps 2..15 is then never taken.  Working on z = -x,
-// bound -minp for the downward case (negation is exact) leaves one code path, whose sweep fuses "add the increment"
-// (:1052-1078 of sweep i), "clip" (:1037-1045 of sweep i+1) and the next weightssum.
-__device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsigned rcbase, double sumc, double& minp, double& maxp) {
-  const double tol_limiter = (double)5e-14f;
-  if (sumc <= 0.0) return;
-  double mass;
-  {
-    double m0 = y[0], m1 = y[1], m2 = y[2], m3 = y[3];
-    TSE_UNROLL
-    for (int n = 4; n < 16; n += 4) {
-      m0 += y[n];
-      m1 += y[n + 1];
-      m2 += y[n + 2];
-      m3 += y[n + 3];
-    }
-    mass = (m0 + m1) + (m2 + m3);
-  }
-  if (mass < minp * sumc) minp = mass / sumc;
-  if (mass > maxp * sumc) maxp = mass / sumc;
-  // any x = y*rc outside [minp, maxp]?  Four predicates OR-accumulate the 32 compares (setp.<cmp>.or), which keeps the
-  // pre-check at DMUL + 2 DSETP per node.
+// 1 if any of the 16 values lies outside [lo, hi].  Four predicates OR-accumulate the 32 compares (setp.<cmp>.or): 2 DSETP per
+// node and no selects.
+__device__ __forceinline__ unsigned any_outside(const double (&x)[16], double lo, double hi) {
   unsigned viol;
-  {
-    double x[16];
-    TSE_UNROLL
-    for (int cc = 0; cc < 8; ++cc) {
-      const double2 r = lds128v(rcbase + cc * GPL * 16);
-      x[2 * cc] = y[2 * cc] * r.x;
-      x[2 * cc + 1] = y[2 * cc + 1] * r.y;
-    }
     asm("{\n"
         ".reg .pred p0, p1, p2, p3;\n"
         "setp.gt.f64 p0, %1, %17;\n    setp.lt.or.f64 p0, %1, %18, p0;\n"
@@ -164,10 +130,55 @@ __device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsig
         "}\n"
         : "=r"(viol)
         : "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]), "d"(x[4]), "d"(x[5]), "d"(x[6]), "d"(x[7]), "d"(x[8]), "d"(x[9]), "d"(x[10]), "d"(x[11]),
-          "d"(x[12]), "d"(x[13]), "d"(x[14]), "d"(x[15]), "d"(maxp), "d"(minp));
+          "d"(x[12]), "d"(x[13]), "d"(x[14]), "d"(x[15]), "d"(hi), "d"(lo));
+  return viol;
+}
+
+// limiter_optim_iter_full (prim_advection_mod.F90:976-1094).  On entry y = c*x (mass contributions, c = sphweights*dpmass);
+// c and rc = 1/c are read from the per-plane package in shared memory (cbase/rcbase = shared address of chunk 0 of this
+// plane, chunk stride GPL*16 bytes).  Sums use 4 interleaved partial accumulators (fixed order, identical on every GPU count).
+//
+// Fast path: mass = sum(y) and the min/max relaxation (:1016-1029) need no x; if no x = y*rc lies outside [minp, maxp] the
+// reference's first sweep finds addmass = 0 and leaves (:1047), so y is returned untouched.
+// Slow path (x in place of y): sweep 1 clips against both bounds.  From then on the direction is fixed: redistributing
+// addmass > 0 raises nodes below maxp, so later sweeps can only find nodes above maxp and addmass stays >= 0 (and the mirror
+// image for addmass < 0); the lower-bound test of the reference's sweeps 2..15 is then never taken.  Working on z = -x,
+// bound -minp for the downward case (negation is exact) leaves one code path, whose sweep fuses "add the increment"
+// (:1052-1078 of sweep i), "clip" (:1037-1045 of sweep i+1) and the next weightssum; the weight of a node is carried in a
+// register and zeroed when the node reaches the bound, which removes the per-node "still below the bound?" tests.
+__device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsigned rcbase, double sumc, double& minp, double& maxp) {
+  const double tol_limiter = (double)5e-14f;
+  if (sumc <= 0.0) return;
+  double mass;
+  {
+    double m0 = y[0], m1 = y[1], m2 = y[2], m3 = y[3];
+    TSE_UNROLL
+    for (int n = 4; n < 16; n += 4) {
+      m0 += y[n];
+      m1 += y[n + 1];
+      m2 += y[n + 2];
+      m3 += y[n + 3];
+    }
+    mass = (m0 + m1) + (m2 + m3);
+  }
+  if (mass < minp * sumc) minp = mass / sumc;
+  if (mass > maxp * sumc) maxp = mass / sumc;
+  // any x = y*rc outside [minp, maxp]?  (DMUL + 2 DSETP per node)
+  unsigned viol;
+  {
+    double x[16];
+    TSE_UNROLL
+    for (int cc = 0; cc < 8; ++cc) {
+      const double2 r = lds128v(rcbase + cc * GPL * 16);
+      x[2 * cc] = y[2 * cc] * r.x;
+      x[2 * cc + 1] = y[2 * cc + 1] * r.y;
+    }
+    viol = any_outside(x, minp, maxp);
   }
   if (!viol) return;
 
+  // ---- slow path ---------------------------------------------------------------------------------------------------
+  // x = y*rc in place of y.  Sweep 1 clips against both bounds (:1037-1045).
   const double thresh = tol_limiter * fabs(mass);
   TSE_UNROLL
   for (int cc = 0; cc < 8; ++cc) {
@@ -175,6 +186,7 @@ __device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsig
     y[2 * cc] *= r.x;
     y[2 * cc + 1] *= r.y;
   }
+  double ce[16];  // c of the nodes that can still be moved towards the bound (0 for the others); c itself until the direction is known
   double am;
   {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -182,6 +194,7 @@ __device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsig
     for (int cc = 0; cc < 8; cc += 2) {
       const double2 ca = lds128v(cbase + cc * GPL * 16), cb = lds128v(cbase + (cc + 1) * GPL * 16);
       const int n = 2 * cc;
+      ce[n] = ca.x; ce[n + 1] = ca.y; ce[n + 2] = cb.x; ce[n + 3] = cb.y;
       double t;
       t = dmin(dmax(y[n], minp), maxp);         a0 = fma(y[n] - t, ca.x, a0);     y[n] = t;
       t = dmin(dmax(y[n + 1], minp), maxp);     a1 = fma(y[n + 1] - t, ca.y, a1); y[n + 1] = t;
@@ -191,6 +204,15 @@ __device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsig
     am = (a0 + a1) + (a2 + a3);
   }
   if (fabs(am) > thresh) {
+    // From here on the direction is fixed (see above); z = x for addmass > 0, z = -x (bound -minp) for addmass < 0.
+    // A node takes part in the redistribution while z < bz.  ce[] carries its weight c while it does and 0 afterwards, so a
+    // sweep needs no test "is this node still below the bound": per node
+    //     t = z + inc                    (:1060, :1072: x = x + addmass/weightssum; nodes at the bound are put back by the clip)
+    //     z = t < bz ? t : bz            (:1037-1040 of the next sweep)
+    //     addmass += ce*(t - z)          ((x - maxp)*c for the clipped nodes, 0 for the others and for nodes that were at the bound)
+    //     ce = t < bz ? ce : 0;  weightssum += ce
+    // which is arithmetically the reference's sequence for every node that moves (t, t - bz and the sums are the same operations
+    // on the same operands); 5 FP64-pipe instructions + 4 selects per node.
     const bool up = am > 0.0;
     const double bz = up ? maxp : -minp;
     if (!up) {
@@ -202,18 +224,18 @@ __device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsig
     {
       double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
       TSE_UNROLL
-      for (int cc = 0; cc < 8; cc += 2) {
-        const double2 ca = lds128v(cbase + cc * GPL * 16), cb = lds128v(cbase + (cc + 1) * GPL * 16);
-        const int n = 2 * cc;
-        if (y[n] < bz) w0 += ca.x;
-        if (y[n + 1] < bz) w1 += ca.y;
-        if (y[n + 2] < bz) w2 += cb.x;
-        if (y[n + 3] < bz) w3 += cb.y;
+      for (int n = 0; n < 16; n += 4) {
+        ce[n] = y[n] < bz ? ce[n] : 0.0;             w0 += ce[n];
+        ce[n + 1] = y[n + 1] < bz ? ce[n + 1] : 0.0; w1 += ce[n + 1];
+        ce[n + 2] = y[n + 2] < bz ? ce[n + 2] : 0.0; w2 += ce[n + 2];
+        ce[n + 3] = y[n + 3] < bz ? ce[n + 3] : 0.0; w3 += ce[n + 3];
       }
       wsum = (w0 + w1) + (w2 + w3);
     }
 #pragma unroll 1
     for (int iter = 1; iter <= NPSQ - 1; ++iter) {
+      // no node left below the bound: the reference divides by zero, moves nothing and leaves at the next test (:1047)
+      if (!(wsum > 0.0)) break;
       const double inc = am / wsum;
       if (iter == NPSQ - 1) {  // the reference's last sweep redistributes without a further clip
         TSE_UNROLL
@@ -222,31 +244,24 @@ __device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsig
         break;
       }
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
-      TSE_UNROLL
-      for (int cc = 0; cc < 8; cc += 2) {
-        const double2 ca = lds128v(cbase + cc * GPL * 16), cb = lds128v(cbase + (cc + 1) * GPL * 16);
-        const double cv[4] = {ca.x, ca.y, cb.x, cb.y};
-        // per node: raise if below the bound, then either clip the overshoot (its mass goes to am) or count the node as still
-        // raisable (its weight goes to wsum).  (ptxas turns each conditional FP64 update into op + 2 FSEL, also when the PTX
-        // is written with predicates.)
-#define TSE_SWEEP_NODE(n, cv, acc, wacc) \
+#define TSE_SWEEP_NODE(n, acc, wacc)     \
   {                                      \
-    double z = y[n];                     \
-    if (z < bz) z += inc;                \
-    const double d = z - bz;             \
-    if (d > 0.0) {                       \
-      acc = fma(d, cv, acc);             \
-      z = bz;                            \
-    }                                    \
-    if (d < 0.0) wacc += cv;             \
+    const double t = y[n] + inc;         \
+    const bool below = t < bz;           \
+    const double z = below ? t : bz;     \
+    acc = fma(ce[n], t - z, acc);        \
+    ce[n] = below ? ce[n] : 0.0;         \
+    wacc += ce[n];                       \
     y[n] = z;                            \
   }
-        TSE_SWEEP_NODE(2 * cc + 0, cv[0], a0, w0)
-        TSE_SWEEP_NODE(2 * cc + 1, cv[1], a1, w1)
-        TSE_SWEEP_NODE(2 * cc + 2, cv[2], a2, w2)
-        TSE_SWEEP_NODE(2 * cc + 3, cv[3], a3, w3)
-#undef TSE_SWEEP_NODE
+      TSE_UNROLL
+      for (int n = 0; n < 16; n += 4) {
+        TSE_SWEEP_NODE(n + 0, a0, w0)
+        TSE_SWEEP_NODE(n + 1, a1, w1)
+        TSE_SWEEP_NODE(n + 2, a2, w2)
+        TSE_SWEEP_NODE(n + 3, a3, w3)
       }
+#undef TSE_SWEEP_NODE
       am = (a0 + a1) + (a2 + a3);
       wsum = (w0 + w1) + (w2 + w3);
       if (am <= thresh) break;
@@ -261,6 +276,49 @@ __device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsig
     const double2 c = lds128v(cbase + cc * GPL * 16);
     y[2 * cc] *= c.x;
     y[2 * cc + 1] *= c.y;
+  }
+}
+
+// Verification hook (tse_debug_limiter): the limiter exactly as the stage kernels call it -- c and 1/c staged in shared memory in
+// the package layout, sumc from 4 interleaved partial sums, y = sphweights*ptens in and out -- on independent planes.
+__global__ void __launch_bounds__(GPL) k_debug_limiter(int n, double* __restrict__ y, const double* __restrict__ sphweights,
+                                                      const double* __restrict__ dpmass, double* __restrict__ minp, double* __restrict__ maxp) {
+  __shared__ __align__(16) unsigned char pk[2 * PP_BYTES];  // CL | RC
+  const int pl = threadIdx.x, p = blockIdx.x * GPL + pl;
+  const bool valid = p < n;
+  double yy[16];
+  TSE_UNROLL
+  for (int c = 0; c < 8; ++c) {
+    double2 cl = make_double2(1.0, 1.0), sw = cl;
+    if (valid) {
+      sw = *reinterpret_cast<const double2*>(sphweights + (size_t)p * 16 + 2 * c);
+      const double2 dm = *reinterpret_cast<const double2*>(dpmass + (size_t)p * 16 + 2 * c);
+      const double2 pt = *reinterpret_cast<const double2*>(y + (size_t)p * 16 + 2 * c);
+      cl = make_double2(sw.x * dm.x, sw.y * dm.y);
+      yy[2 * c] = sw.x * pt.x;
+      yy[2 * c + 1] = sw.y * pt.y;
+    } else {
+      yy[2 * c] = yy[2 * c + 1] = 0.0;
+    }
+    *reinterpret_cast<double2*>(pk + (c * GPL + pl) * 16) = cl;
+    *reinterpret_cast<double2*>(pk + PP_BYTES + (c * GPL + pl) * 16) = make_double2(1.0 / cl.x, 1.0 / cl.y);
+  }
+  __syncthreads();
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  TSE_UNROLL
+  for (int c = 0; c < 8; c += 2) {
+    const double2 x0 = lds128(pk, (c * GPL + pl) * 16), x1 = lds128(pk, ((c + 1) * GPL + pl) * 16);
+    s0 += x0.x; s1 += x0.y; s2 += x1.x; s3 += x1.y;
+  }
+  const double sumc = (s0 + s1) + (s2 + s3);
+  double mn = valid ? minp[p] : 0.0, mx = valid ? maxp[p] : 0.0;
+  const unsigned base = (unsigned)__cvta_generic_to_shared(pk) + pl * 16;
+  limiter_y(yy, base, base + PP_BYTES, sumc, mn, mx);
+  if (valid) {
+    TSE_UNROLL
+    for (int c = 0; c < 8; ++c) *reinterpret_cast<double2*>(y + (size_t)p * 16 + 2 * c) = make_double2(yy[2 * c], yy[2 * c + 1]);
+    minp[p] = mn;
+    maxp[p] = mx;
   }
 }
 
@@ -335,37 +393,54 @@ __device__ __forceinline__ void laplace_wk_el(const double (&s)[16], const Dvv& 
   }
 }
 
-// min/max over the element and its up to 8 neighbours (neighbor_minmax, viscosity_mod.F90:748-816), one thread per plane scalar
+// min/max over the element and its up to 8 neighbours (neighbor_minmax, viscosity_mod.F90:748-816).  One thread per (element,
+// level chunk, tracer): the KC = 4 levels of a chunk are contiguous (32 bytes = one sector) both in the per-plane extrema
+// arrays and in the ghost bundles, so every neighbour costs two 16-byte loads per array instead of four 8-byte ones.
+static_assert(KC == 4 && NLEV % KC == 0, "k_nbr_minmax reads the 4 levels of a chunk as two double2");
 __global__ void __launch_bounds__(256) k_nbr_minmax(Geo G, int Q, const double* __restrict__ lmin, const double* __restrict__ lmax,
                                                     const double* __restrict__ ghost_mm, double* __restrict__ qmin,
                                                     double* __restrict__ qmax) {
-  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)G.ngroups * NKC * Q * GPL;
-  if (p >= total) return;
-  const int kk = p % KC, el = (p / KC) % GE;
-  const size_t r = p / GPL;
-  const int q = r % Q;
-  const size_t gk = r / Q;
+  const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // index of (g, kc, q, el) in layout order
+  const size_t total = (size_t)G.ngroups * NKC * Q * GE;
+  if (r >= total) return;
+  const int el = r % GE;
+  const size_t r2 = r / GE;
+  const int q = r2 % Q;
+  const size_t gk = r2 / Q;
   const int kc = gk % NKC, g = gk / NKC;
-  const int e = g * GE + el, k = kc * KC + kk;
+  const int e = g * GE + el;
   if (e >= G.nelem) return;
-  double mn = lmin[p], mx = lmax[p];
-  const int* nb = G.nbr8 + (size_t)e * 8;
+  const double2* mn2 = reinterpret_cast<const double2*>(lmin + r * KC);
+  const double2* mx2 = reinterpret_cast<const double2*>(lmax + r * KC);
+  double2 mna = mn2[0], mnb = mn2[1], mxa = mx2[0], mxb = mx2[1];
+  const int4* nb4 = reinterpret_cast<const int4*>(G.nbr8 + (size_t)e * 8);
+  const int4 n0 = nb4[0], n1 = nb4[1];
+  const int nb[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+  // branch-free: an absent neighbour reads the element itself (min/max with itself changes nothing), so that all 32 loads are
+  // independent and go out together -- the kernel is latency bound
+  const double2 *pn[8], *px[8];
   TSE_UNROLL
   for (int d = 0; d < 8; ++d) {
     const int b = nb[d];
-    if (b >= 0) {
-      const size_t pb = qplane(b, q, k, Q);
-      mn = dmin(mn, lmin[pb]);
-      mx = dmax(mx, lmax[pb]);
-    } else if (b <= -2) {
-      const size_t gb = ((size_t)(-b - 2) * 2 * Q + q) * NLEV + k;
-      mn = dmin(mn, ghost_mm[gb]);
-      mx = dmax(mx, ghost_mm[gb + (size_t)Q * NLEV]);
-    }
+    const size_t pb = b >= 0 ? qplane(b, q, kc * KC, Q) : r * KC;
+    const size_t gb = ((size_t)(b <= -2 ? -b - 2 : 0) * 2 * Q + q) * NLEV + kc * KC;
+    pn[d] = reinterpret_cast<const double2*>(b <= -2 ? ghost_mm + gb : lmin + pb);
+    px[d] = reinterpret_cast<const double2*>(b <= -2 ? ghost_mm + gb + (size_t)Q * NLEV : lmax + pb);
   }
-  qmin[p] = mn;
-  qmax[p] = mx;
+  double2 va[8][4];
+  TSE_UNROLL
+  for (int d = 0; d < 8; ++d) {
+    va[d][0] = pn[d][0]; va[d][1] = pn[d][1]; va[d][2] = px[d][0]; va[d][3] = px[d][1];
+  }
+  TSE_UNROLL
+  for (int d = 0; d < 8; ++d) {
+    mna.x = dmin(mna.x, va[d][0].x); mna.y = dmin(mna.y, va[d][0].y); mnb.x = dmin(mnb.x, va[d][1].x); mnb.y = dmin(mnb.y, va[d][1].y);
+    mxa.x = dmax(mxa.x, va[d][2].x); mxa.y = dmax(mxa.y, va[d][2].y); mxb.x = dmax(mxb.x, va[d][3].x); mxb.y = dmax(mxb.y, va[d][3].y);
+  }
+  double2* on = reinterpret_cast<double2*>(qmin + r * KC);
+  double2* ox = reinterpret_cast<double2*>(qmax + r * KC);
+  on[0] = mna; on[1] = mnb;
+  ox[0] = mxa; ox[1] = mxb;
 }
 
 }  // namespace tse
