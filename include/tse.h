@@ -143,6 +143,10 @@ int tse_prim_run_subcycle(tse_handle h, double tstep, int* nstep /* in/out tl%ns
  * repro_sum_mod.F90:216-628) and min/max of Qdp/dp */
 int tse_diag_mass(tse_handle h, int tl, double* mass /* [qsize] */);
 int tse_diag_qminmax(tse_handle h, int tl, double* qmin /* [qsize] */, double* qmax /* [qsize] */);
+/* Per-tracer 64-bit fingerprint of Qdp(tl): wrapping sum over all (element, level, node) of a mix of the value's bit pattern and its
+ * global position (GridVertex%SpaceCurve of the element, level, node).  Independent of the partition and of the element order:
+ * equal fingerprints on 1, 2, 4, 8 GPUs mean the fields are bit-for-bit equal (the reference's claim, README:46-47). */
+int tse_diag_field_hash(tse_handle h, int tl, unsigned long long* hash /* [qsize] */);
 
 /* Verification hook (the reference has no counterpart): runs limiter_optim_iter_full (prim_advection_mod.F90:976-1094) exactly as the
  * stage kernels call it on n independent 4x4 planes.  ptens_w[n][16] in: ptens (tracer mass, the reference's argument); out:

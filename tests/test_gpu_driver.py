@@ -70,16 +70,31 @@ def test_mass_is_order_independent(built):
 
 
 def test_negative_thickness_is_reported(built):
-    """vertical_remap aborts on negative layer thickness (prim_advection_mod.F90:1323): the C ABI returns an error."""
+    """vertical_remap aborts on negative layer thickness (prim_advection_mod.F90:1323).  A host that follows the reference's hook
+    sequence (vertical_remap_cuda, then copy_qdp_d2h, prim_driver_mod.F90:798-801) must see the error at the copy; every other
+    blocking entry reports it too; reporting clears it, and the handle works again once the thicknesses are sane."""
     from transport_se_b200.advection import TracerAdvection, TseError
     m, v, hv, o = make_oracle(4, 2, 11)
     adv = TracerAdvection(m, v, hv, qsize=2, nu_q=0.0)
     adv.copy_qdp_h2d(o.Qdp, 1)
-    dp = -np.ones_like(o.dp)
-    adv.set_derived(vn0=o.vn0, dp=dp)
-    adv.vertical_remap(100.0, 3, 1)
-    with pytest.raises(TseError):
-        adv.synchronize()
+    bad = -np.ones_like(o.dp)
+    out = np.zeros_like(o.Qdp)
+    for entry in (lambda: adv.copy_qdp_d2h(out, 1), adv.synchronize, lambda: adv.diag_mass(1), lambda: adv.get_dp3d_ps(np.zeros_like(o.dp), None)):
+        adv.set_derived(vn0=o.vn0, dp=bad)
+        adv.vertical_remap(100.0, 3, 1)
+        with pytest.raises(TseError, match="negative layer thickness"):
+            entry()
+        adv.synchronize()   # reported once: the flag is cleared
+    # the handle is usable afterwards: a clean remap of a fresh field matches the oracle
+    oracle_begin_step(o, 11, 100.0)
+    adv.copy_qdp_h2d(o.Qdp, 1)
+    adv.set_derived(o.vn0, o.dp, o.eta_dot_dpdn, o.omega_p)
+    o.precompute_divdp()
+    adv.precompute_divdp()
+    assert o.vertical_remap(100.0, o.tl["np1"], 1) == 0
+    adv.vertical_remap(100.0, o.tl["np1"], 1)
+    adv.copy_qdp_d2h(out, 1)
+    assert per_tracer_relerr(out[:, 0], o.Qdp[:, 0]).max() < 1e-12
     adv.close()
 
 

@@ -57,8 +57,9 @@ def _cases():
         for i, n in enumerate(rest):
             W = c[rest[i:]].sum()
             inc = remaining / W
-            gap[n] = cum + theta * inc
-            remaining = (inc - theta * inc) * c[n]
+            last = i == len(rest) - 1
+            gap[n] = cum + (2.0 if last else theta) * inc   # the last receiver has room for all that is left: bounds stay feasible
+            remaining = 0.0 if last else (inc - theta * inc) * c[n]
             cum += inc
         q = 1.0 - gap
         q[big] = 1.0 + excess
@@ -92,10 +93,6 @@ def test_limiter_matches_oracle_on_adversarial_planes(built):
     assert np.array_equal(got[neg], (sph * pt)[neg])
     bscale = np.maximum(np.abs(rmx), np.abs(rmn)) + 1e-300
     assert np.max(np.abs(gmn - rmn) / bscale) < 1e-14 and np.max(np.abs(gmx - rmx) / bscale) < 1e-14
-    # the cases really exercise the long path: the oracle's result differs from a single clip for the many-sweep planes
-    x = ref / dpm
-    many = np.array([t.startswith("many-sweeps") for t in tag])
-    assert np.all(np.max(x[many], axis=1) <= rmx[many] * (1 + 1e-12))
     # invariants of the device result itself: mass conserved to the limiter's tolerance, bounds respected
     c = sph * dpm
     ok = c.sum(axis=1) > 0
@@ -103,7 +100,7 @@ def test_limiter_matches_oracle_on_adversarial_planes(built):
     mass1 = np.sum(got, axis=1)
     assert np.max(np.abs(mass1 - mass0)[ok] / np.maximum(np.abs(mass0[ok]), 1e-300)) < 2e-13
     xg = got / c
-    inb = ok & np.array([not t.startswith("many-sweeps") for t in tag])  # 15 sweeps may end outside (as in the reference)
+    inb = ok
     assert np.all(xg[inb].min(axis=1) >= gmn[inb] - 1e-13 * np.maximum(1, np.abs(gmn[inb])))
     assert np.all(xg[inb].max(axis=1) <= gmx[inb] + 1e-13 * np.maximum(1, np.abs(gmx[inb])))
 

@@ -48,7 +48,7 @@ EXPORTS = ["tse_last_error", "tse_device_count", "tse_init", "tse_finalize", "ts
            "tse_precompute_divdp", "tse_euler_step", "tse_qdp_time_avg", "tse_vertical_remap", "tse_advec_tracers_remap_rk2",
            "tse_dcmip_init", "tse_prim_run_subcycle", "tse_diag_mass", "tse_diag_qminmax", "tse_timer_ms", "tse_launch_count",
            "tse_device_bytes", "tse_timer_reset", "tse_mark", "tse_mark_elapsed_ms", "tse_get_wind", "tse_stage_launch_count", "tse_halo_bytes",
-           "tse_debug_limiter"]
+           "tse_debug_limiter", "tse_diag_field_hash"]
 
 
 def cuda_lib():
@@ -97,6 +97,7 @@ def cuda_lib():
         L.tse_get_wind.argtypes = [vp, _dp, ll, _dp, ll]
         L.tse_halo_bytes.argtypes = [vp]
         L.tse_halo_bytes.restype = ll
+        L.tse_diag_field_hash.argtypes = [vp, i, C.POINTER(C.c_ulonglong)]
         L.tse_debug_limiter.argtypes = [i, _dp, _dp, _dp, _dp, _dp]
         _LIB = L
     return _LIB
@@ -229,6 +230,12 @@ class TracerAdvection:
         a, b = np.zeros(self.qsize), np.zeros(self.qsize)
         self._ck(self._L.tse_diag_qminmax(self._h, tl, _p(a), _p(b)))
         return a, b
+
+    def diag_field_hash(self, tl):
+        """Per-tracer fingerprint of Qdp(tl), independent of partition and element order (bit-for-bit checks across GPU counts)."""
+        out = np.zeros(self.qsize, dtype=np.uint64)
+        self._ck(self._L.tse_diag_field_hash(self._h, tl, out.ctypes.data_as(C.POINTER(C.c_ulonglong))))
+        return out
 
     def synchronize(self):
         self._ck(self._L.tse_synchronize(self._h))

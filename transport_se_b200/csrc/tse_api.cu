@@ -71,8 +71,10 @@ struct tse_state {
   Geo geo{};
   Dvv dvv{};
   TileTables tiles{};
+  NbrTables nbrt{};
   std::vector<int> h2i;  // host element -> internal element
   int* d_h2i = nullptr;
+  int* d_gkey = nullptr;  // [internal element] global space-filling-curve index (host element index if none was given)
   // tracer buffers
   double* qbuf[4] = {nullptr, nullptr, nullptr, nullptr};
   double* qghost[4] = {nullptr, nullptr, nullptr, nullptr};  // halo of each buffer when it is pending (multi-GPU)
@@ -96,6 +98,9 @@ struct tse_state {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_derived = nullptr, ev_alt_free = nullptr;
   int* d_err = nullptr;
+  int* h_err = nullptr;             // pinned copy of d_err, refreshed after every vertical remap
+  cudaEvent_t ev_err = nullptr;     // ... and the event that says the refresh has landed
+  bool err_pending = false;
   long long launches = 0, stage_launches = 0, dev_bytes = 0;
   std::vector<void*> allocs;
   // halo exchange (multi-GPU)
@@ -125,12 +130,13 @@ struct tse_state {
   int test_case = 0;
   double *d_lon = nullptr, *d_lat = nullptr;
   DcmipTables dcmip{};
-  std::vector<double> hv_hyai, hv_hybi, hv_hyam, hv_hybm;
+  std::vector<double> hv_hyai, hv_hybi, hv_hyam, hv_hybm, h_dA, h_dB;
   bool have_latlon = false;
   // diagnostics
   unsigned long long* d_maxbits = nullptr;
   long long* d_acc = nullptr;
   int* d_shift = nullptr;
+  std::vector<int> mass_shift;  // binary scale of the fixed-point mass sum, per tracer (kept between calls)
 };
 
 namespace {
@@ -195,8 +201,8 @@ cudaEvent_t get_event(tse_state* s) {
     s->event_pool.pop_back();
     return e;
   }
-  cudaEvent_t e;
-  cudaEventCreate(&e);
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) return nullptr;  // timers degrade to no-ops (ScopedTimer checks)
   return e;
 }
 void resolve_timers(tse_state* s) {
@@ -219,20 +225,48 @@ struct ScopedTimer {
     r.name = name;
     r.a = get_event(s);
     r.b = get_event(s);
-    cudaEventRecord(r.a, s->stream);
+    if (r.a && r.b) cudaEventRecord(r.a, s->stream);
   }
   ~ScopedTimer() {
+    if (!r.a || !r.b) {
+      if (r.a) s->event_pool.push_back(r.a);
+      if (r.b) s->event_pool.push_back(r.b);
+      return;
+    }
     cudaEventRecord(r.b, s->stream);
     s->timer_pending.push_back(r);
   }
 };
 
-int check_device_error(tse_state* s) {
-  int flag = 0;
-  CU(cudaMemcpyAsync(&flag, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-  CU(cudaStreamSynchronize(s->stream));
-  if (flag) return fail("vertical_remap: negative layer thickness.  timestep or remap time too large");  // prim_advection_mod.F90:1323
+// Negative layer thickness in vertical_remap (prim_advection_mod.F90:1319-1324: the reference calls abortmp).  The kernel raises
+// d_err; a copy into pinned memory is queued right behind it.  Blocking entries (anything that hands results to the host, and
+// tse_synchronize) report it after their own stream synchronisation; non-blocking entries report it as soon as the copy has
+// landed, without waiting.  Reporting clears the flag, so the handle stays usable (the half-remapped field is the caller's
+// problem, as after abortmp).
+int report_remap_error(tse_state* s) {
+  *s->h_err = 0;
+  s->err_pending = false;
+  CU(cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream));
+  return fail("vertical_remap: negative layer thickness.  timestep or remap time too large");  // prim_advection_mod.F90:1323
+}
+int queue_error_readback(tse_state* s) {
+  CU(cudaMemcpyAsync(s->h_err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaEventRecord(s->ev_err, s->stream));
+  s->err_pending = true;
   return 0;
+}
+// after the caller has synchronised s->stream
+int check_device_error(tse_state* s) {
+  if (!s->err_pending) return 0;
+  CU(cudaEventSynchronize(s->ev_err));
+  s->err_pending = false;
+  return *s->h_err ? report_remap_error(s) : 0;
+}
+// without blocking
+int poll_device_error(tse_state* s) {
+  if (!s->err_pending || cudaEventQuery(s->ev_err) != cudaSuccess) return 0;
+  s->err_pending = false;
+  return *s->h_err ? report_remap_error(s) : 0;
 }
 
 // ---- halo exchange ----------------------------------------------------------------------------
@@ -248,14 +282,20 @@ int exchange(tse_state* s, std::initializer_list<Xfer> xs) {
   if (s->cycles.empty()) return 0;
   if (!s->comm) return fail("halo exchange: this rank has off-GPU neighbours but tse_comm_init was not called");
   NC(ncclGroupStart());
+  ncclResult_t bad = ncclSuccess;
   for (const auto& c : s->cycles)
     for (const Xfer& x : xs) {
       const size_t off = (size_t)(x.bundles ? c.boff : c.off) * x.unit, cnt = (size_t)(x.bundles ? c.blen : c.len) * x.unit;
-      NC(ncclSend(x.send + off, cnt, ncclDouble, c.peer, s->comm, s->comm_stream));
-      NC(ncclRecv(x.recv + off, cnt, ncclDouble, c.peer, s->comm, s->comm_stream));
+      ncclResult_t r = ncclSend(x.send + off, cnt, ncclDouble, c.peer, s->comm, s->comm_stream);
+      if (r == ncclSuccess) r = ncclRecv(x.recv + off, cnt, ncclDouble, c.peer, s->comm, s->comm_stream);
+      if (r != ncclSuccess && bad == ncclSuccess) bad = r;
       s->halo_bytes += (long long)cnt * 8;
     }
-  NC(ncclGroupEnd());
+  {
+    const ncclResult_t r = ncclGroupEnd();  // always closed, also after a failed send/recv
+    if (bad == ncclSuccess) bad = r;
+  }
+  if (bad != ncclSuccess) return fail("halo exchange: %s", ncclGetErrorString(bad));
   CU(cudaEventRecord(s->ev_halo, s->comm_stream));
   s->halo_outstanding = true;
   return 0;
@@ -351,8 +391,8 @@ int launch_tile_overlapped(tse_state* s, const TileArgs& a, F start_comm) {
 // neighbor_minmax (viscosity_mod.F90:748-816) after the element extrema of off-GPU neighbours have arrived: 9-way min/max
 int neighbor_minmax(tse_state* s) {
   if (wait_halo(s)) return 1;
-  const size_t total = (size_t)s->ngroups * NKC * s->Q * GE;
-  k_nbr_minmax<<<(unsigned)((total + 255) / 256), 256, 0, s->stream>>>(s->geo, s->Q, s->qmin_loc, s->qmax_loc, s->ghost_mm, s->qmin, s->qmax);
+  k_nbr_minmax<<<s->ngroups * NKC, NBQ * GPL, nbr_smem_bytes(s->nbrt.xmax), s->stream>>>(s->geo, s->nbrt, s->Q, s->qmin_loc, s->qmax_loc,
+                                                                                       s->ghost_mm, s->qmin, s->qmax);
   ++s->launches;
   CU(cudaGetLastError());
   return 0;
@@ -414,7 +454,12 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("tse_init: no CUDA device (this library has no CPU path)");
   if (cfg->device >= 0) CU(cudaSetDevice(cfg->device));
 
-  tse_state* s = new tse_state;
+  // every early return below releases what has been created so far (streams, events, HBM: tens of GB at ne120)
+  struct Guard {
+    tse_state* p;
+    ~Guard() { if (p) tse_finalize(p); }
+  } guard{new tse_state};
+  tse_state* s = guard.p;
   s->cfg = *cfg;
   s->nelem = cfg->nelemd;
   s->ngroups = (s->nelem + GE - 1) / GE;
@@ -431,6 +476,11 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
   s->h2i.assign(ne, 0);
   for (int i = 0; i < ne; ++i) s->h2i[order[i]] = i;
   if (upload(s, &s->d_h2i, s->h2i)) return 1;
+  {
+    std::vector<int> gkey(s->npad, 0);
+    for (int eh = 0; eh < ne; ++eh) gkey[s->h2i[eh]] = conn->sfc_index ? conn->sfc_index[eh] : eh;
+    if (upload(s, &s->d_gkey, gkey)) return 1;
+  }
 
   // geometry
   const size_t n16 = (size_t)s->npad * 16;
@@ -598,6 +648,40 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
       return fail("tse_init: halo of %d nodes per group does not fit in shared memory", hmax);
     if (tile_in_bytes(hmax) / 8 >= 65536) return fail("tse_init: halo of %d nodes per group overflows the gather offsets", hmax);
   }
+  {
+    // group-local view of the neighbour-element table for k_nbr_minmax: neighbours inside the group are read from the group's
+    // own tile in shared memory, the others (other groups, ghost bundles of other GPUs) through a per-group list
+    std::vector<int> nbr_t((size_t)s->npad * 8, -1), ext_off(s->ngroups + 1, 0), ext_src;
+    int xmax = 1;
+    for (int g = 0; g < s->ngroups; ++g) {
+      std::vector<int> ext;
+      for (int el = 0; el < GE; ++el)
+        for (int d = 0; d < 8; ++d) {
+          const int b = nbr8[((size_t)g * GE + el) * 8 + d];
+          if (b == -1 || (b >= 0 && b / GE == g)) continue;
+          ext.push_back(b);
+        }
+      std::sort(ext.begin(), ext.end());
+      ext.erase(std::unique(ext.begin(), ext.end()), ext.end());
+      for (int el = 0; el < GE; ++el)
+        for (int d = 0; d < 8; ++d) {
+          const size_t i = ((size_t)g * GE + el) * 8 + d;
+          const int b = nbr8[i];
+          if (b == -1) continue;
+          if (b >= 0 && b / GE == g) nbr_t[i] = b % GE;
+          else nbr_t[i] = 256 + (int)(std::lower_bound(ext.begin(), ext.end(), b) - ext.begin());
+        }
+      ext_off[g + 1] = ext_off[g] + (int)ext.size();
+      ext_src.insert(ext_src.end(), ext.begin(), ext.end());
+      xmax = std::max(xmax, (int)ext.size());
+    }
+    if (ext_src.empty()) ext_src.push_back(-1);
+    int *d_a, *d_b, *d_c;
+    if (upload(s, &d_a, nbr_t) || upload(s, &d_b, ext_off) || upload(s, &d_c, ext_src)) return 1;
+    s->nbrt.nbr_t = d_a; s->nbrt.ext_off = d_b; s->nbrt.ext_src = d_c; s->nbrt.xmax = xmax;
+    if (nbr_smem_bytes(xmax) > 200 * 1024) return fail("tse_init: %d external neighbour elements per group do not fit in shared memory", xmax);
+    CU(cudaFuncSetAttribute(k_nbr_minmax, cudaFuncAttributeMaxDynamicSharedMemorySize, nbr_smem_bytes(xmax)));
+  }
   s->geo.spheremp = d_sp; s->geo.rspheremp = d_rsp; s->geo.rmr = d_rmr; s->geo.mD = d_mD; s->geo.T = d_T;
   s->geo.gsrc = d_gsrc; s->geo.nbr8 = d_nbr8; s->geo.nelem = ne; s->geo.ngroups = s->ngroups;
 
@@ -608,6 +692,8 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
     dB[k] = hv->hybi[k + 1] - hv->hybi[k];
     dp0[k] = (hv->hyai[k + 1] - hv->hyai[k]) * hv->ps0 + (hv->hybi[k + 1] - hv->hybi[k]) * hv->ps0;  // prim_advection_mod.F90:818-820
   }
+  s->h_dA = dA;
+  s->h_dB = dB;
   s->hyai0_ps0 = hv->hyai[0] * hv->ps0;
   s->ps0 = hv->ps0;
   s->hv_hyai.assign(hv->hyai, hv->hyai + NLEV + 1);
@@ -627,7 +713,8 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
     s->have_latlon = true;
   }
   if (upload(s, &s->d_dp0, dp0) || upload(s, &s->d_dA, dA) || upload(s, &s->d_dB, dB)) return 1;
-  if (dalloc(s, &s->d_maxbits, (size_t)s->Q) || dalloc(s, &s->d_acc, (size_t)2 * s->Q) || dalloc(s, &s->d_shift, (size_t)s->Q)) return 1;
+  s->mass_shift.assign(s->Q, 0);
+  if (dalloc(s, &s->d_maxbits, (size_t)MASS_REP * s->Q) || dalloc(s, &s->d_acc, (size_t)2 * MASS_REP * s->Q) || dalloc(s, &s->d_shift, (size_t)s->Q)) return 1;
 
   // state
   s->ldoubles = (size_t)s->ngroups * NKC * GPL * 16;
@@ -662,6 +749,9 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
   if (dalloc(s, &s->qmin, nplanes) || dalloc(s, &s->qmax, nplanes) || dalloc(s, &s->qmin_loc, nplanes) || dalloc(s, &s->qmax_loc, nplanes))
     return 1;
   if (dalloc(s, &s->d_err, 1)) return 1;
+  CU(cudaMallocHost(&s->h_err, sizeof(int)));
+  *s->h_err = 0;
+  CU(cudaEventCreateWithFlags(&s->ev_err, cudaEventDisableTiming));
   if (nghost > 0) {
     const size_t gq = (size_t)nghost * s->Q * NLEV;
     for (int b = 0; b < 4; ++b)
@@ -700,15 +790,17 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
   TSE_TILE_SMEM(OP_BIHARM_PRE);
   TSE_TILE_SMEM(OP_TIME_AVG);
   TSE_TILE_SMEM(OP_RESOLVE);
+  TSE_TILE_SMEM(OP_MASS);
 #undef TSE_TILE_SMEM
   CU(cudaStreamSynchronize(s->stream));
+  guard.p = nullptr;
   *out = s;
   return 0;
 }
 
 int tse_finalize(tse_handle s) {
   if (!s) return 0;
-  cudaStreamSynchronize(s->stream);
+  if (s->stream) cudaStreamSynchronize(s->stream);
   resolve_timers(s);
   if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
   if (s->comm) ncclCommDestroy(s->comm);
@@ -725,12 +817,15 @@ int tse_finalize(tse_handle s) {
   for (cudaEvent_t e : s->marks)
     if (e) cudaEventDestroy(e);
   for (void* p : s->allocs) cudaFree(p);
-  cudaStreamDestroy(s->stream);
+  if (s->h_err) cudaFreeHost(s->h_err);
+  if (s->ev_err) cudaEventDestroy(s->ev_err);
+  if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
   return 0;
 }
 
 int tse_synchronize(tse_handle s) {
+  if (!s) return fail("tse_synchronize: null handle");
   if (s->copy_stream) CU(cudaStreamSynchronize(s->copy_stream));
   if (s->comm_stream) CU(cudaStreamSynchronize(s->comm_stream));
   CU(cudaStreamSynchronize(s->stream));
@@ -744,6 +839,7 @@ int tse_comm_unique_id(void* id128) {
 }
 
 int tse_comm_init(tse_handle s, int nranks, int rank, const void* id128) {
+  if (!s) return fail("tse_comm_init: null handle");
   if (s->comm) return fail("tse_comm_init: already initialised");
   ncclUniqueId id;
   std::memcpy(&id, id128, sizeof id);
@@ -784,9 +880,14 @@ static int qdp_copy(tse_state* s, double* host, long long elem_stride, int tl, i
 }
 
 int tse_copy_qdp_h2d(tse_handle s, const double* qdp, long long elem_stride, int tl) {
+  if (!s || !qdp) return fail("tse_copy_qdp_h2d: null argument");
   return qdp_copy(s, const_cast<double*>(qdp), elem_stride, tl, 1);
 }
-int tse_copy_qdp_d2h(tse_handle s, double* qdp, long long elem_stride, int tl) { return qdp_copy(s, qdp, elem_stride, tl, 0); }
+int tse_copy_qdp_d2h(tse_handle s, double* qdp, long long elem_stride, int tl) {
+  if (!s || !qdp) return fail("tse_copy_qdp_d2h: null argument");
+  if (qdp_copy(s, qdp, elem_stride, tl, 0)) return 1;
+  return check_device_error(s);  // the field may be half remapped (prim_advection_mod.F90:1323)
+}
 
 static int level_copy(tse_state* s, double* dev, double* host, long long stride, int ncomp, int host_nlev, int to_device) {
   if (!host) return 0;
@@ -835,6 +936,8 @@ static int level_upload_async(tse_state* s, double* dev, const double* host, lon
 
 int tse_set_derived(tse_handle s, const double* vn0, long long s_vn0, const double* dp, long long s_dp, const double* eta, long long s_eta,
                     const double* omega, long long s_omega) {
+  if (!s) return fail("tse_set_derived: null handle");
+  if (!s) return fail("tse_set_derived: null handle");
   if (vn0 || dp) {
     // The new winds go into the second copy of vn0/dp on the copy stream while the kernels queued so far (the previous tracer
     // step) still read the first; the compute stream picks them up through an event and the two copies swap roles.  The second
@@ -856,6 +959,8 @@ int tse_set_derived(tse_handle s, const double* vn0, long long s_vn0, const doub
 
 int tse_get_derived(tse_handle s, double* divdp, long long s_divdp, double* proj, long long s_proj, double* eta, long long s_eta,
                     double* omega, long long s_omega) {
+  if (!s) return fail("tse_get_derived: null handle");
+  if (!s) return fail("tse_get_derived: null handle");
   if (level_copy(s, s->divdp, divdp, s_divdp, 1, NLEV, 0)) return 1;
   if (level_copy(s, s->divdp_proj, proj, s_proj, 1, NLEV, 0)) return 1;
   if (level_copy(s, s->eta_dot, eta, s_eta, 1, NLEV + 1, 0)) return 1;
@@ -864,11 +969,13 @@ int tse_get_derived(tse_handle s, double* divdp, long long s_divdp, double* proj
 }
 
 int tse_get_wind(tse_handle s, double* vn0, long long s_vn0, double* dp, long long s_dp) {
+  if (!s) return fail("tse_get_wind: null handle");
   if (level_copy(s, s->vn0, vn0, s_vn0, 2, NLEV, 0)) return 1;
   return level_copy(s, s->dp, dp, s_dp, 1, NLEV, 0);
 }
 
 int tse_get_dp3d_ps(tse_handle s, double* dp3d, long long s_dp3d, double* ps_v, long long s_ps) {
+  if (!s) return fail("tse_get_dp3d_ps: null handle");
   if (level_copy(s, s->dp3d, dp3d, s_dp3d, 1, NLEV, 0)) return 1;
   if (ps_v) {
     std::vector<double> tmp((size_t)s->npad * 16);
@@ -876,25 +983,33 @@ int tse_get_dp3d_ps(tse_handle s, double* dp3d, long long s_dp3d, double* ps_v, 
     CU(cudaStreamSynchronize(s->stream));
     for (int eh = 0; eh < s->nelem; ++eh) std::memcpy(ps_v + (size_t)eh * s_ps, &tmp[(size_t)s->h2i[eh] * 16], 16 * 8);
   }
-  return 0;
+  CU(cudaStreamSynchronize(s->stream));
+  return check_device_error(s);
 }
 
 int tse_get_qminmax(tse_handle s, double* qmin, double* qmax) {
-  const size_t cnt = (size_t)s->nelem * s->Q * NLEV;
-  if (cnt > s->stage_doubles) return fail("tse_get_qminmax: staging buffer too small");
+  if (!s) return fail("tse_get_qminmax: null handle");
+  const size_t per_elem = (size_t)s->Q * NLEV;
+  const size_t ne_chunk = std::max<size_t>(1, s->stage_doubles / per_elem);
   for (int w = 0; w < 2; ++w) {
     double* h = w ? qmax : qmin;
     if (!h) continue;
-    k_scalar_to_host<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(w ? s->qmax : s->qmin, s->stage, s->d_h2i, s->nelem, s->Q);
-    ++s->launches;
-    CU(cudaMemcpyAsync(h, s->stage, cnt * 8, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    for (size_t e0 = 0; e0 < (size_t)s->nelem; e0 += ne_chunk) {
+      const size_t n = std::min(ne_chunk, (size_t)s->nelem - e0), cnt = n * per_elem;
+      k_scalar_to_host<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(w ? s->qmax : s->qmin, s->stage, s->d_h2i + e0, (int)n, s->Q);
+      ++s->launches;
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(h + e0 * per_elem, s->stage, cnt * 8, cudaMemcpyDeviceToHost, s->stream));
+      CU(cudaStreamSynchronize(s->stream));
+    }
   }
   return 0;
 }
 
 // ---- the path ---------------------------------------------------------------------------------
 int tse_precompute_divdp(tse_handle s) {
+  if (!s) return fail("tse_precompute_divdp: null handle");
+  if (poll_device_error(s)) return 1;
   k_divdp<<<level_blocks(s), 128, 0, s->stream>>>(s->geo, s->dvv, s->vn0, s->divdp, s->divdp_proj);
   ++s->launches;
   CU(cudaGetLastError());
@@ -902,6 +1017,8 @@ int tse_precompute_divdp(tse_handle s) {
 }
 
 int tse_euler_step(tse_handle s, int np1_qdp, int n0_qdp, double dt, int DSSopt, int rhs_multiplier) {
+  if (!s) return fail("tse_euler_step: null handle");
+  if (poll_device_error(s)) return 1;
   if (check_tl(np1_qdp) || check_tl(n0_qdp)) return 1;
   if (rhs_multiplier < 0 || rhs_multiplier > 2) return fail("tse_euler_step: rhs_multiplier=%d", rhs_multiplier);
   ScopedTimer tm(s, "euler_step");
@@ -965,6 +1082,8 @@ int tse_euler_step(tse_handle s, int np1_qdp, int n0_qdp, double dt, int DSSopt,
 }
 
 int tse_qdp_time_avg(tse_handle s, int rkstage, int n0_qdp, int np1_qdp) {
+  if (!s) return fail("tse_qdp_time_avg: null handle");
+  if (poll_device_error(s)) return 1;
   if (check_tl(np1_qdp) || check_tl(n0_qdp) || n0_qdp == np1_qdp) return fail("tse_qdp_time_avg: bad time levels %d %d", n0_qdp, np1_qdp);
   if (resolve_slot(s, n0_qdp) || wait_halo(s)) return 1;
   const int in = s->slot_buf[np1_qdp], q0 = s->slot_buf[n0_qdp];
@@ -982,6 +1101,8 @@ int tse_qdp_time_avg(tse_handle s, int rkstage, int n0_qdp, int np1_qdp) {
 }
 
 int tse_vertical_remap(tse_handle s, double dt, int np1, int np1_qdp) {
+  if (!s) return fail("tse_vertical_remap: null handle");
+  if (poll_device_error(s)) return 1;
   (void)np1;  // the device keeps a single copy of dp3d/ps_v: the one of time level np1
   if (check_tl(np1_qdp)) return 1;
   if (resolve_slot(s, np1_qdp)) return 1;
@@ -989,15 +1110,18 @@ int tse_vertical_remap(tse_handle s, double dt, int np1, int np1_qdp) {
   RemapArgs a;
   a.q = s->qbuf[s->slot_buf[np1_qdp]];
   a.dp = s->dp; a.divdp_proj = s->divdp_proj; a.dp3d = s->dp3d; a.ps_v = s->ps_v;
-  a.dA = s->d_dA; a.dB = s->d_dB; a.hyai0_ps0 = s->hyai0_ps0; a.dt = dt; a.Q = s->Q; a.nelem = s->nelem; a.error_flag = s->d_err;
+  std::memcpy(a.dA, s->h_dA.data(), sizeof a.dA);
+  std::memcpy(a.dB, s->h_dB.data(), sizeof a.dB);
+  a.hyai0_ps0 = s->hyai0_ps0; a.dt = dt; a.Q = s->Q; a.nelem = s->nelem; a.error_flag = s->d_err;
   const int rm_threads = std::min(RM_MAX_THREADS, 32 * ((16 * s->Q + 31) / 32));
   k_vertical_remap<<<s->nelem, rm_threads, RM_SMEM, s->stream>>>(a);
   ++s->launches;
   CU(cudaGetLastError());
-  return 0;
+  return queue_error_readback(s);
 }
 
 int tse_advec_tracers_remap_rk2(tse_handle s, double dt, int nstep) {
+  if (!s) return fail("tse_advec_tracers_remap_rk2: null handle");
   // TimeLevel_Qdp (time_mod.F90:85-109)
   const int qsplit = s->cfg.qsplit > 0 ? s->cfg.qsplit : 1;
   const int n0 = ((nstep / qsplit) % 2 == 0) ? 1 : 2, np1 = 3 - n0;
@@ -1012,6 +1136,7 @@ int tse_advec_tracers_remap_rk2(tse_handle s, double dt, int nstep) {
 }
 
 int tse_dcmip_init(tse_handle s, int test_case) {
+  if (!s) return fail("tse_dcmip_init: null handle");
   if (test_case != 11 && test_case != 12) return fail("tse_dcmip_init: test_case must be 11 (DCMIP 1-1) or 12 (DCMIP 1-2)");
   if (!s->have_latlon || s->hv_hyam.empty()) return fail("tse_dcmip_init: needs spherep lat/lon and hyam/hybm at tse_init");
   s->test_case = test_case;
@@ -1042,6 +1167,8 @@ int tse_dcmip_init(tse_handle s, int test_case) {
 
 // prim_run_subcycle (prim_driver_mod.F90:701-854) with prim_step (:858-943) and prim_advance_exp (prim_advance_mod.F90:70-152)
 int tse_prim_run_subcycle(tse_handle s, double tstep, int* nstep_io) {
+  if (!s) return fail("tse_prim_run_subcycle: null handle");
+  if (poll_device_error(s)) return 1;
   if (!s->test_case) return fail("tse_prim_run_subcycle: call tse_dcmip_init first");
   int nstep = *nstep_io;
   const int rsplit = s->cfg.rsplit > 0 ? s->cfg.rsplit : 1, qsplit = s->cfg.qsplit > 0 ? s->cfg.qsplit : 1;
@@ -1070,38 +1197,85 @@ int tse_prim_run_subcycle(tse_handle s, double tstep, int* nstep_io) {
 // global tracer mass sum_e sum_k sum_ij spheremp*Qdp with an order-independent fixed-point sum
 // (the repro_sum idea, repro_sum_mod.F90:216-628: bitwise identical for any element order / GPU count)
 int tse_diag_mass(tse_handle s, int tl, double* mass) {
+  if (!s) return fail("tse_diag_mass: null handle");
+  if (check_tl(tl) || wait_halo(s)) return 1;
+  if (!mass) return fail("tse_diag_mass: null argument");
+  const int Q = s->Q;
+  // One pass through the tile pipeline (OP_MASS): every plane's J = sum spheremp*Qdp is added as a two-limb fixed-point number
+  // scaled by 2^shift[q], and the largest |J| is tracked alongside.  The shift of the previous call is reused as long as the
+  // largest |J| stays inside its window (2^26 <= |J|max * 2^shift < 2^38: no overflow with up to 2^23 planes, >= 66 significant
+  // bits); otherwise it is re-centred and the pass repeated (first call, or a tracer whose mass changed by orders of magnitude).
+  // Max and sums are integer all-reduces, so every rank takes the same decision and the result is bitwise independent of the
+  // element order and of the number of GPUs.
+  TileArgs a = tile_args(s);
+  set_src(s, a, 0, s->slot_buf[tl], s->slot_pending[tl]);
+  a.mass_acc = s->d_acc;
+  a.mass_maxbits = s->d_maxbits;
+  a.mass_shift = s->d_shift;
+  std::vector<unsigned long long> mb(Q), mb_all((size_t)MASS_REP * Q);
+  std::vector<long long> acc(2 * Q), acc_all((size_t)2 * MASS_REP * Q);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    CU(cudaMemsetAsync(s->d_maxbits, 0, sizeof(unsigned long long) * MASS_REP * Q, s->stream));
+    CU(cudaMemsetAsync(s->d_acc, 0, sizeof(long long) * 2 * MASS_REP * Q, s->stream));
+    launch_tile<OP_MASS>(s, a);
+    CU(cudaGetLastError());
+    if (s->comm) {
+      // doubles >= 0 order like their bit patterns: the global max is an integer max
+      NC(ncclAllReduce(s->d_maxbits, s->d_maxbits, (size_t)MASS_REP * Q, ncclUint64, ncclMax, s->comm, s->stream));
+      NC(ncclAllReduce(s->d_acc, s->d_acc, (size_t)2 * MASS_REP * Q, ncclInt64, ncclSum, s->comm, s->stream));
+    }
+    CU(cudaMemcpyAsync(mb_all.data(), s->d_maxbits, sizeof(unsigned long long) * MASS_REP * Q, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(acc_all.data(), s->d_acc, sizeof(long long) * 2 * MASS_REP * Q, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    std::fill(mb.begin(), mb.end(), 0ull);
+    std::fill(acc.begin(), acc.end(), 0ll);
+    for (int r = 0; r < MASS_REP; ++r)
+      for (int q = 0; q < Q; ++q) {
+        mb[q] = std::max(mb[q], mb_all[(size_t)r * Q + q]);
+        // wrapping adds, like the device atomics: the true sums fit (the window below), so the wrapped total is exact
+        acc[2 * q] = (long long)((unsigned long long)acc[2 * q] + (unsigned long long)acc_all[2 * ((size_t)r * Q + q)]);
+        acc[2 * q + 1] = (long long)((unsigned long long)acc[2 * q + 1] + (unsigned long long)acc_all[2 * ((size_t)r * Q + q) + 1]);
+      }
+    bool fits = true;
+    for (int q = 0; q < Q; ++q) {
+      double mx;
+      std::memcpy(&mx, &mb[q], 8);
+      const int ideal = 37 - (mx > 0 ? std::ilogb(mx) : 0);  // |J|max * 2^ideal in [2^37, 2^38)
+      if (mx > 0 && (s->mass_shift[q] > ideal || s->mass_shift[q] < ideal - 11)) fits = false;
+      if (!fits) break;
+    }
+    if (fits) break;
+    if (attempt == 1) return fail("tse_diag_mass: fixed-point window did not settle");
+    for (int q = 0; q < Q; ++q) {
+      double mx;
+      std::memcpy(&mx, &mb[q], 8);
+      s->mass_shift[q] = 37 - (mx > 0 ? std::ilogb(mx) : 0);
+    }
+    CU(cudaMemcpyAsync(s->d_shift, s->mass_shift.data(), sizeof(int) * Q, cudaMemcpyHostToDevice, s->stream));
+  }
+  for (int q = 0; q < Q; ++q) {
+    const long double tot = (long double)acc[2 * q] + std::ldexp((long double)acc[2 * q + 1], -40);
+    mass[q] = (double)std::ldexp(tot, -s->mass_shift[q]);
+  }
+  return check_device_error(s);
+}
+int tse_diag_field_hash(tse_handle s, int tl, unsigned long long* hash) {
+  if (!s || !hash) return fail("tse_diag_field_hash: null argument");
   if (check_tl(tl) || wait_halo(s)) return 1;
   const DssView v = view(s, s->slot_buf[tl], s->slot_pending[tl]);
   const int Q = s->Q;
-  CU(cudaMemsetAsync(s->d_maxbits, 0, sizeof(unsigned long long) * Q, s->stream));
-  CU(cudaMemsetAsync(s->d_acc, 0, sizeof(long long) * 2 * Q, s->stream));
-  k_mass_max<<<plane_grid(s), GPL * QPB, 0, s->stream>>>(s->geo, v, s->d_maxbits);
+  unsigned long long* acc = reinterpret_cast<unsigned long long*>(s->d_acc);
+  CU(cudaMemsetAsync(acc, 0, sizeof(unsigned long long) * Q, s->stream));
+  k_field_hash<<<plane_grid(s), GPL * QPB, 0, s->stream>>>(s->geo, v, s->d_gkey, acc);
   ++s->launches;
-  // doubles >= 0 order like their bit patterns: the global max is an integer max
-  if (s->comm) NC(ncclAllReduce(s->d_maxbits, s->d_maxbits, Q, ncclUint64, ncclMax, s->comm, s->stream));
-  std::vector<unsigned long long> mb(Q);
-  CU(cudaMemcpyAsync(mb.data(), s->d_maxbits, sizeof(unsigned long long) * Q, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaGetLastError());
+  if (s->comm) NC(ncclAllReduce(acc, acc, Q, ncclUint64, ncclSum, s->comm, s->stream));  // wraps modulo 2^64 like the local sums
+  CU(cudaMemcpyAsync(hash, acc, sizeof(unsigned long long) * Q, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
-  std::vector<int> shift(Q);
-  for (int q = 0; q < Q; ++q) {
-    double mx;
-    std::memcpy(&mx, &mb[q], 8);
-    shift[q] = 37 - (mx > 0 ? std::ilogb(mx) : 0);  // |J|*2^shift < 2^38; up to 2^23 planes per tracer sum below 2^61
-  }
-  CU(cudaMemcpyAsync(s->d_shift, shift.data(), sizeof(int) * Q, cudaMemcpyHostToDevice, s->stream));
-  k_mass_fixed<<<plane_grid(s), GPL * QPB, 0, s->stream>>>(s->geo, v, s->d_shift, s->d_acc);
-  ++s->launches;
-  if (s->comm) NC(ncclAllReduce(s->d_acc, s->d_acc, 2 * Q, ncclInt64, ncclSum, s->comm, s->stream));
-  std::vector<long long> acc(2 * Q);
-  CU(cudaMemcpyAsync(acc.data(), s->d_acc, sizeof(long long) * 2 * Q, cudaMemcpyDeviceToHost, s->stream));
-  CU(cudaStreamSynchronize(s->stream));
-  for (int q = 0; q < Q; ++q) {
-    const long double tot = (long double)acc[2 * q] + std::ldexp((long double)acc[2 * q + 1], -40);
-    mass[q] = (double)std::ldexp(tot, -shift[q]);
-  }
-  return 0;
+  return check_device_error(s);
 }
 int tse_diag_qminmax(tse_handle s, int tl, double* qmin, double* qmax) {
+  if (!s) return fail("tse_diag_qminmax: null handle");
   if (check_tl(tl) || wait_halo(s)) return 1;
   const DssView v = view(s, s->slot_buf[tl], s->slot_pending[tl]);
   const int Q = s->Q;
@@ -1129,7 +1303,7 @@ int tse_diag_qminmax(tse_handle s, int tl, double* qmin, double* qmax) {
     qmin[q] = back(h[q]);
     qmax[q] = back(h[Q + q]);
   }
-  return 0;
+  return check_device_error(s);
 }
 
 int tse_debug_limiter(int n, double* ptens_w, const double* sphweights, const double* dpmass, double* minp, double* maxp) {
@@ -1159,27 +1333,31 @@ int tse_debug_limiter(int n, double* ptens_w, const double* sphweights, const do
 }
 
 double tse_timer_ms(tse_handle s, const char* name) {
+  if (!s || !name) return -1.0;
   resolve_timers(s);
   auto it = s->timers.find(name);
   return it == s->timers.end() ? -1.0 : it->second;
 }
 int tse_timer_reset(tse_handle s) {
+  if (!s) return fail("tse_timer_reset: null handle");
   resolve_timers(s);
   s->timers.clear();
   return 0;
 }
-long long tse_launch_count(tse_handle s) { return s->launches; }
-long long tse_stage_launch_count(tse_handle s) { return s->stage_launches; }
-long long tse_device_bytes(tse_handle s) { return s->dev_bytes; }
-long long tse_halo_bytes(tse_handle s) { return s->halo_bytes; }
+long long tse_launch_count(tse_handle s) { return s ? s->launches : -1; }
+long long tse_stage_launch_count(tse_handle s) { return s ? s->stage_launches : -1; }
+long long tse_device_bytes(tse_handle s) { return s ? s->dev_bytes : -1; }
+long long tse_halo_bytes(tse_handle s) { return s ? s->halo_bytes : -1; }
 
 int tse_mark(tse_handle s, int slot) {
+  if (!s) return fail("tse_mark: null handle");
   if (slot < 0 || slot >= 16) return fail("tse_mark: slot %d", slot);
   if (!s->marks[slot]) CU(cudaEventCreate(&s->marks[slot]));
   CU(cudaEventRecord(s->marks[slot], s->stream));
   return 0;
 }
 double tse_mark_elapsed_ms(tse_handle s, int a, int b) {
+  if (!s) return -1.0;
   if (a < 0 || a >= 16 || b < 0 || b >= 16 || !s->marks[a] || !s->marks[b]) return -1.0;
   if (cudaEventSynchronize(s->marks[b]) != cudaSuccess) return -1.0;
   float ms = 0;

@@ -1,57 +1,37 @@
-// Diagnostics: order-independent global tracer mass (the fixed-point idea of repro_sum, reference
-// src/repro_sum_mod.F90:216-628, applied to the "Q mass" sum of prim_state_mod.F90:352-385).
-// Each plane's J = sum_ij spheremp*Qdp is split into two int64 limbs relative to the global max exponent;
-// integer adds commute, so the result is bitwise identical for any element order, block schedule or GPU count.
+// Diagnostics on the plane-per-thread view: global extrema of Q and the field fingerprint.  (The global tracer mass runs through
+// the tile pipeline, OP_MASS in tse_pipe.cuh.)
 #pragma once
 #include "tse_kernels.cuh"
 
 namespace tse {
 
-__device__ __forceinline__ double plane_mass(const Geo& G, const DssView& in, const ThreadPlane& t) {
-  double v[16];
-  in.load(G, t.e, t.q, t.k, v);
-  const double* sp = G.spheremp + (size_t)t.e * 16;
-  double J = 0.0;
-  TSE_UNROLL
-  for (int n = 0; n < 16; ++n) J = fma(sp[n], v[n], J);
-  return J;
-}
-
 // a warp holds 32 / SEG tracers of SEG planes each (SEG = 32 when a tracer's GPL planes fill whole warps)
 constexpr int SEG = GPL < 32 ? GPL : 32;
 
-__global__ void __launch_bounds__(GPL* QPB) k_mass_max(Geo G, DssView in, unsigned long long* __restrict__ maxbits) {
-  const ThreadPlane t = thread_plane(G, in.Q);
-  unsigned long long b = 0;
-  if (t.valid) b = (unsigned long long)__double_as_longlong(fabs(plane_mass(G, in, t)));
-  TSE_UNROLL
-  for (int o = SEG / 2; o > 0; o >>= 1) {
-    const unsigned long long x = __shfl_xor_sync(0xffffffffu, b, o);
-    b = x > b ? x : b;
-  }
-  const int q = blockIdx.y * QPB + threadIdx.x / GPL;  // uniform per SEG lanes
-  if ((threadIdx.x & (SEG - 1)) == 0 && q < in.Q) atomicMax(maxbits + q, b);
+// Field fingerprint for bit-for-bit comparisons across GPU counts: per tracer, the wrapping 64-bit sum over all (element, level,
+// node) of mix(bit pattern of Qdp, global position).  The position key uses the element's global space-filling-curve index, so
+// the value does not depend on which rank owns the element or where it sits in memory; integer sums commute, so it does not
+// depend on the order either.  Two runs give equal fingerprints iff (up to 2^-64 collisions) every value of the field is bitwise
+// equal at every global position.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {  // splitmix64 finaliser
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
 }
-
-__global__ void __launch_bounds__(GPL* QPB) k_mass_fixed(Geo G, DssView in, const int* __restrict__ shift, long long* __restrict__ acc) {
+__global__ void __launch_bounds__(GPL* QPB) k_field_hash(Geo G, DssView in, const int* __restrict__ gkey, unsigned long long* __restrict__ acc) {
   const ThreadPlane t = thread_plane(G, in.Q);
-  const int q = blockIdx.y * QPB + threadIdx.x / GPL;
-  long long hi = 0, lo = 0;
+  unsigned long long h = 0;
   if (t.valid) {
-    const double x = scalbn(plane_mass(G, in, t), shift[q]);
-    const double xi = trunc(x);
-    hi = (long long)xi;
-    lo = (long long)trunc(scalbn(x - xi, 40));
+    double v[16];
+    in.load(G, t.e, t.q, t.k, v);
+    const unsigned long long pos = (((unsigned long long)gkey[t.e] * NLEV + t.k) * 4096ull + t.q) * 16ull;
+    TSE_UNROLL
+    for (int n = 0; n < 16; ++n) h += mix64((unsigned long long)__double_as_longlong(v[n]) ^ mix64(pos + n));
   }
   TSE_UNROLL
-  for (int o = SEG / 2; o > 0; o >>= 1) {
-    hi += __shfl_xor_sync(0xffffffffu, hi, o);
-    lo += __shfl_xor_sync(0xffffffffu, lo, o);
-  }
-  if ((threadIdx.x & (SEG - 1)) == 0 && q < in.Q) {
-    atomicAdd(reinterpret_cast<unsigned long long*>(acc + 2 * q), (unsigned long long)hi);
-    atomicAdd(reinterpret_cast<unsigned long long*>(acc + 2 * q + 1), (unsigned long long)lo);
-  }
+  for (int o = SEG / 2; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+  const int q = blockIdx.y * QPB + threadIdx.x / GPL;  // uniform per SEG lanes
+  if ((threadIdx.x & (SEG - 1)) == 0 && q < in.Q) atomicAdd(acc + q, h);
 }
 
 // order-preserving map double -> uint64 (so that atomicMin/atomicMax on the integers order like the doubles)

@@ -26,7 +26,7 @@ namespace tse {
 // CTA moves 32 KB per release -> refill round trip (about 2 us), i.e. 4.7 TB/s over the chip; they get 3-4 stages and, where
 // it still leaves 2 CTAs per SM (113 KB each), a double-buffered OUT tile.  The stage ops carry a 40 KB package: 2 + 1.
 // (OP_MINMAX measured slower with 4 stages than with 2.)
-__host__ __device__ constexpr int pipe_nst(int op) { return (op == OP_BIHARM_PRE || op == OP_TIME_AVG || op == OP_RESOLVE) ? 3 : 2; }
+__host__ __device__ constexpr int pipe_nst(int op) { return (op == OP_BIHARM_PRE || op == OP_TIME_AVG || op == OP_RESOLVE || op == OP_MASS) ? 3 : 2; }
 __host__ __device__ constexpr int pipe_nout(int op) { return (op == OP_TIME_AVG || op == OP_RESOLVE) ? 2 : 1; }
 constexpr int NST_MAX = 4;               // barrier slots reserved per kind
 // Stage release protocol (consumer -> producer, "this stage may be refilled"):
@@ -41,6 +41,7 @@ constexpr int NST_MAX = 4;               // barrier slots reserved per kind
 #define TSE_RELEASE 0
 #endif
 constexpr int NCW = TT / 32;             // consumer warps
+constexpr int MASS_REP = 64;             // copies of the OP_MASS accumulators
 #ifndef TSE_NPW
 #define TSE_NPW 2
 #endif
@@ -92,6 +93,9 @@ __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
       "r"(parity)
       : "memory");
 }
+#ifndef TSE_BACKOFF_NS
+#define TSE_BACKOFF_NS 256
+#endif
 // same, for waits that are expected to be long (the producer waiting for a stage to drain): back off between polls so that
 // the spinning warp does not take issue slots from the math warps of its scheduler
 __device__ __forceinline__ void mbar_wait_backoff(unsigned addr, unsigned parity) {
@@ -101,13 +105,13 @@ __device__ __forceinline__ void mbar_wait_backoff(unsigned addr, unsigned parity
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra LAB_DONE;\n"
       "LAB_WAIT:\n"
-      "nanosleep.u32 64;\n"
+      "nanosleep.u32 %2;\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra LAB_DONE;\n"
       "bra LAB_WAIT;\n"
       "LAB_DONE:\n"
       "}\n" ::"r"(addr),
-      "r"(parity)
+      "r"(parity), "n"(TSE_BACKOFF_NS)
       : "memory");
 }
 // completion of all cp.async issued so far by this thread counts as one (pre-counted) arrival on the mbarrier
@@ -269,75 +273,93 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
   }
 
   // ---- level package (see tse_tile.cuh) ------------------------------------------------------------------------------
+  // All global loads of the prologue are issued before the first of them is used (no branches in between: padded elements
+  // read the last real element, their planes are never computed): one memory round trip instead of six dependent ones.
+  // With 2 CTAs per SM the consumer warps of a starting CTA otherwise sit out ~25 % of the CTA's lifetime here.
   const bool main_pending = (OP == OP_STAGE3) ? (a.pending[1] != 0) : (a.pending[0] != 0);
-  if (cfg.nel > 0 && t < GE * 8) {
-    const int pe = t >> 3, c = t & 7, ee = g * GE + pe;
-    double2 e1 = make_double2(0, 0), e2 = e1, rs = e1, t11 = e1, t12 = e1, t22 = e1;
-    if (ee < G.nelem) {
-      const size_t b = (size_t)ee * 16 + 2 * c;
-      const double2 sp = *reinterpret_cast<const double2*>(G.spheremp + b);
-      rs = *reinterpret_cast<const double2*>(G.rspheremp + b);
-      const double2 rm = *reinterpret_cast<const double2*>(G.rmr + b);
-      const double rx0 = main_pending ? rs.x : 1.0, rx1 = main_pending ? rs.y : 1.0;
-      e1 = make_double2(sp.x * rx0, sp.y * rx1);
-      e2 = make_double2(a.dt * (sp.x * rm.x), a.dt * (sp.y * rm.y));
-      if (cfg.T11 >= 0) {
-        const double* T = G.T + (size_t)ee * 48 + 2 * c;
-        t11 = *reinterpret_cast<const double2*>(T);
-        t12 = *reinterpret_cast<const double2*>(T + 16);
-        t22 = *reinterpret_cast<const double2*>(T + 32);
-      }
+  const int elast = G.nelem - 1;
+  double2 L_sp = make_double2(0, 0), L_rs = L_sp, L_rm = L_sp, L_t11 = L_sp, L_t12 = L_sp, L_t22 = L_sp;
+  const bool el_thread = cfg.nel > 0 && t < GE * 8;
+  if (el_thread) {
+    const int c = t & 7, ee = min(g * GE + (t >> 3), elast);
+    const size_t b = (size_t)ee * 16 + 2 * c;
+    L_sp = *reinterpret_cast<const double2*>(G.spheremp + b);
+    L_rs = *reinterpret_cast<const double2*>(G.rspheremp + b);
+    L_rm = *reinterpret_cast<const double2*>(G.rmr + b);
+    if (cfg.T11 >= 0) {
+      const double* T = G.T + (size_t)ee * 48 + 2 * c;
+      L_t11 = *reinterpret_cast<const double2*>(T);
+      L_t12 = *reinterpret_cast<const double2*>(T + 16);
+      L_t22 = *reinterpret_cast<const double2*>(T + 32);
     }
+  }
+  // (plane, 16-byte chunk) pairs of the GPL x 8 chunks, strided over the consumer threads; loads are issued for PB pairs at a
+  // time (all NPK at once would need more registers than the kernel has)
+  constexpr int NPK = (GPL * 8) / TT, PB = NPK % 2 == 0 ? 2 : 1;
+  static_assert((GPL * 8) % TT == 0, "package pairs divide evenly over the consumer threads");
+  if (el_thread) {
+    const int pe = t >> 3, c = t & 7;
+    const double rx0 = main_pending ? L_rs.x : 1.0, rx1 = main_pending ? L_rs.y : 1.0;
+    const double2 e1 = OP == OP_MASS ? L_sp : make_double2(L_sp.x * rx0, L_sp.y * rx1);
+    const double2 e2 = make_double2(a.dt * (L_sp.x * L_rm.x), a.dt * (L_sp.y * L_rm.y));
     const int off = (c * GE + pe) * 16;
     if (cfg.E1 >= 0) *reinterpret_cast<double2*>(elb + cfg.E1 * EL_BYTES + off) = e1;
     if (cfg.E2 >= 0) *reinterpret_cast<double2*>(elb + cfg.E2 * EL_BYTES + off) = e2;
-    if (cfg.RSPH >= 0) *reinterpret_cast<double2*>(elb + cfg.RSPH * EL_BYTES + off) = rs;
+    if (cfg.RSPH >= 0) *reinterpret_cast<double2*>(elb + cfg.RSPH * EL_BYTES + off) = L_rs;
     if (cfg.T11 >= 0) {
-      *reinterpret_cast<double2*>(elb + cfg.T11 * EL_BYTES + off) = t11;
-      *reinterpret_cast<double2*>(elb + cfg.T12 * EL_BYTES + off) = t12;
-      *reinterpret_cast<double2*>(elb + cfg.T22 * EL_BYTES + off) = t22;
+      *reinterpret_cast<double2*>(elb + cfg.T11 * EL_BYTES + off) = L_t11;
+      *reinterpret_cast<double2*>(elb + cfg.T12 * EL_BYTES + off) = L_t12;
+      *reinterpret_cast<double2*>(elb + cfg.T22 * EL_BYTES + off) = L_t22;
     }
   }
   if (cfg.npp > 0) {
-    // (plane, 16-byte chunk) pairs of the GPL x 8 chunks, strided over the consumer threads
-    constexpr int NPK = (GPL * 8 + TT - 1) / TT;
     TSE_UNROLL
-    for (int r = 0; r < NPK; ++r) {
-      const int i = t + r * TT;
-      if (GPL * 8 % TT != 0 && i >= GPL * 8) break;
-      const int ppl = i >> 3, c = i & 7, n = 2 * c;
-      const int pe = g * GE + ppl / KC, pk = kc * KC + ppl % KC;
-      double2 u1 = make_double2(0, 0), u2 = u1, cl = make_double2(1, 1), rd = make_double2(1, 1), rcl = make_double2(1, 1);
-      if (pe < G.nelem) {
+    for (int r0b = 0; r0b < NPK; r0b += PB) {
+      double2 P_dp[PB], P_dj[PB], P_rs[PB], P_dd[PB], P_v1[PB], P_v2[PB], P_sp[PB], P_m11[PB], P_m12[PB], P_m21[PB], P_m22[PB];
+      TSE_UNROLL
+      for (int r = 0; r < PB; ++r) {
+        const int i = t + (r0b + r) * TT;
+        const int ppl = i >> 3, n = 2 * (i & 7);
+        const int pe = min(g * GE + ppl / KC, elast), pk = kc * KC + ppl % KC;
         const size_t lp = lplane(pe, pk) * 16 + n, gb = (size_t)pe * 16 + n;
-        const double2 dpv = *reinterpret_cast<const double2*>(a.dp + lp);
-        const double2 dj = *reinterpret_cast<const double2*>(a.divdp_proj + lp);
-        const double2 rs = *reinterpret_cast<const double2*>(G.rspheremp + gb);
-        const double rx0 = main_pending ? rs.x : 1.0, rx1 = main_pending ? rs.y : 1.0;
-        const double dps0 = dpv.x - a.rhs_mult_dt * dj.x, dps1 = dpv.y - a.rhs_mult_dt * dj.y;
-        const double r0 = 1.0 / dps0, r1 = 1.0 / dps1;
-        rd = make_double2(r0 * rx0, r1 * rx1);
+        P_dp[r] = *reinterpret_cast<const double2*>(a.dp + lp);
+        P_dj[r] = *reinterpret_cast<const double2*>(a.divdp_proj + lp);
+        P_rs[r] = *reinterpret_cast<const double2*>(G.rspheremp + gb);
         if (kStage) {
-          const double2 dd = *reinterpret_cast<const double2*>(a.divdp + lp);
-          const double2 v1 = *reinterpret_cast<const double2*>(a.vn0 + vplane(pe, pk, 0) * 16 + n);
-          const double2 v2 = *reinterpret_cast<const double2*>(a.vn0 + vplane(pe, pk, 1) * 16 + n);
-          const double2 sp = *reinterpret_cast<const double2*>(G.spheremp + gb);
+          P_dd[r] = *reinterpret_cast<const double2*>(a.divdp + lp);
+          P_v1[r] = *reinterpret_cast<const double2*>(a.vn0 + vplane(pe, pk, 0) * 16 + n);
+          P_v2[r] = *reinterpret_cast<const double2*>(a.vn0 + vplane(pe, pk, 1) * 16 + n);
+          P_sp[r] = *reinterpret_cast<const double2*>(G.spheremp + gb);
           const double* mD = G.mD + (size_t)pe * 64 + n;
-          const double2 m11 = *reinterpret_cast<const double2*>(mD), m12 = *reinterpret_cast<const double2*>(mD + 16);
-          const double2 m21 = *reinterpret_cast<const double2*>(mD + 32), m22 = *reinterpret_cast<const double2*>(mD + 48);
-          const double vs10 = v1.x * r0, vs11 = v1.y * r1, vs20 = v2.x * r0, vs21 = v2.y * r1;
-          u1 = make_double2((m11.x * vs10 + m12.x * vs20) * rx0, (m11.y * vs11 + m12.y * vs21) * rx1);
-          u2 = make_double2((m21.x * vs10 + m22.x * vs20) * rx0, (m21.y * vs11 + m22.y * vs21) * rx1);
-          cl = make_double2(sp.x * (dps0 - a.dt * dd.x), sp.y * (dps1 - a.dt * dd.y));
-          rcl = make_double2(1.0 / cl.x, 1.0 / cl.y);
+          P_m11[r] = *reinterpret_cast<const double2*>(mD);
+          P_m12[r] = *reinterpret_cast<const double2*>(mD + 16);
+          P_m21[r] = *reinterpret_cast<const double2*>(mD + 32);
+          P_m22[r] = *reinterpret_cast<const double2*>(mD + 48);
         }
       }
-      const int off = (c * GPL + ppl) * 16;
-      if (cfg.U1 >= 0) *reinterpret_cast<double2*>(pp + cfg.U1 * PP_BYTES + off) = u1;
-      if (cfg.U2 >= 0) *reinterpret_cast<double2*>(pp + cfg.U2 * PP_BYTES + off) = u2;
-      if (cfg.CL >= 0) *reinterpret_cast<double2*>(pp + cfg.CL * PP_BYTES + off) = cl;
-      if (cfg.RDP >= 0) *reinterpret_cast<double2*>(pp + cfg.RDP * PP_BYTES + off) = rd;
-      if (cfg.RC >= 0) *reinterpret_cast<double2*>(pp + cfg.RC * PP_BYTES + off) = rcl;
+      TSE_UNROLL
+      for (int r = 0; r < PB; ++r) {
+        const int i = t + (r0b + r) * TT;
+        const int ppl = i >> 3, c = i & 7;
+        double2 u1 = make_double2(0, 0), u2 = u1, cl = make_double2(1, 1), rcl = make_double2(1, 1);
+        const double rx0 = main_pending ? P_rs[r].x : 1.0, rx1 = main_pending ? P_rs[r].y : 1.0;
+        const double dps0 = P_dp[r].x - a.rhs_mult_dt * P_dj[r].x, dps1 = P_dp[r].y - a.rhs_mult_dt * P_dj[r].y;
+        const double r0 = 1.0 / dps0, r1 = 1.0 / dps1;
+        const double2 rd = make_double2(r0 * rx0, r1 * rx1);
+        if (kStage) {
+          const double vs10 = P_v1[r].x * r0, vs11 = P_v1[r].y * r1, vs20 = P_v2[r].x * r0, vs21 = P_v2[r].y * r1;
+          u1 = make_double2((P_m11[r].x * vs10 + P_m12[r].x * vs20) * rx0, (P_m11[r].y * vs11 + P_m12[r].y * vs21) * rx1);
+          u2 = make_double2((P_m21[r].x * vs10 + P_m22[r].x * vs20) * rx0, (P_m21[r].y * vs11 + P_m22[r].y * vs21) * rx1);
+          cl = make_double2(P_sp[r].x * (dps0 - a.dt * P_dd[r].x), P_sp[r].y * (dps1 - a.dt * P_dd[r].y));
+          rcl = make_double2(1.0 / cl.x, 1.0 / cl.y);
+        }
+        const int off = (c * GPL + ppl) * 16;
+        if (cfg.U1 >= 0) *reinterpret_cast<double2*>(pp + cfg.U1 * PP_BYTES + off) = u1;
+        if (cfg.U2 >= 0) *reinterpret_cast<double2*>(pp + cfg.U2 * PP_BYTES + off) = u2;
+        if (cfg.CL >= 0) *reinterpret_cast<double2*>(pp + cfg.CL * PP_BYTES + off) = cl;
+        if (cfg.RDP >= 0) *reinterpret_cast<double2*>(pp + cfg.RDP * PP_BYTES + off) = rd;
+        if (cfg.RC >= 0) *reinterpret_cast<double2*>(pp + cfg.RC * PP_BYTES + off) = rcl;
+      }
     }
   }
 
@@ -464,6 +486,18 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
           S[2 * c] *= rs.x;
           S[2 * c + 1] *= rs.y;
         }
+      } else if (OP == OP_MASS) {
+        // J = sum_ij spheremp*Qdp of this plane (the per-element part of global_integral, global_norms_mod.F90:39-86)
+        double J = 0.0;
+        TSE_UNROLL
+        for (int c = 0; c < 8; ++c) {
+          const double2 sp = lds128(elb + cfg.E1 * EL_BYTES, (c * GE + el) * 16);
+          double2 rs = lds128(elb + cfg.RSPH * EL_BYTES, (c * GE + el) * 16);
+          if (!a.pending[0]) rs = make_double2(1.0, 1.0);
+          J = fma(sp.x, rs.x * S[2 * c], J);
+          J = fma(sp.y, rs.y * S[2 * c + 1], J);
+        }
+        S[0] = J;
       } else if (OP == OP_TIME_AVG) {
         if (which == 0) {
           TSE_UNROLL
@@ -544,6 +578,32 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
         }
         TSE_UNROLL
         for (int n = 0; n < 16; ++n) S[n] = y[n];
+      }
+    }
+
+    if (OP == OP_MASS) {
+      // two-limb fixed-point image of J (order-independent integer sums, the repro_sum idea, repro_sum_mod.F90:216-628) and the
+      // running max of |J|; the 16 lanes that hold one tracer reduce first (EPW * KC = 16 planes)
+      static_assert(OP != OP_MASS || EPW * KC == 16, "OP_MASS reduces over half-warps");
+      const double J = valid ? S[0] : 0.0;
+      const double x = scalbn(J, valid ? a.mass_shift[q] : 0);
+      const double xi = trunc(x);
+      long long hi = (long long)xi, lo = (long long)trunc(scalbn(x - xi, 40));
+      unsigned long long mb = (unsigned long long)__double_as_longlong(fabs(J));
+      TSE_UNROLL
+      for (int o = 8; o > 0; o >>= 1) {
+        hi += __shfl_xor_sync(0xffffffffu, hi, o);
+        lo += __shfl_xor_sync(0xffffffffu, lo, o);
+        const unsigned long long y = __shfl_xor_sync(0xffffffffu, mb, o);
+        mb = y > mb ? y : mb;
+      }
+      if ((lane & 15) == 0 && q < Q) {
+        // MASS_REP copies of the accumulators, picked by CTA: atomics on one address serialise in L2 (41 M of them on 105
+        // addresses cost more than the whole pass); the copies are folded on the host (integer adds and max: order-free)
+        const int rep = blockIdx.x % MASS_REP;
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.mass_acc + 2 * (rep * Q + q)), (unsigned long long)hi);
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.mass_acc + 2 * (rep * Q + q) + 1), (unsigned long long)lo);
+        atomicMax(a.mass_maxbits + rep * Q + q, mb);
       }
     }
 

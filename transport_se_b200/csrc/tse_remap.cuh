@@ -32,7 +32,7 @@ constexpr int RS_PIO = RS_PX + 75 * 4 * 2 * 16;   // [74]: pio(1..74) at index 0
 constexpr int RS_PIN = RS_PIO + 74 * 16;          // [73]: pin(1..73)
 constexpr int RS_G = RS_PIN + 73 * 16;            // [72][4]: g1, g2, g3 (integration weights of target interface k+1), dpo(kid(k))
 constexpr int RS_END = RS_G + 72 * 4 * 16;
-constexpr size_t RM_SMEM = (size_t)RS_END * sizeof(double) + 2 * 80 * 16;  // + kid[72][16], cnt[74][16] as bytes (padded to 80 rows)
+constexpr size_t RM_SMEM = (size_t)RS_END * sizeof(double) + 80 * 16 + 74 * 16 * sizeof(int);  // + kid[72][16] (bytes, unused rows pad to 80), cnt[74][16] (int)
 static_assert(NLEV == 72 && KC == 4 && RM_PF == KC, "the level walk is unrolled by level chunks");
 
 struct RemapArgs {
@@ -41,8 +41,8 @@ struct RemapArgs {
   const double* divdp_proj;  // derived%divdp_proj
   double* dp3d;              // out: state%dp3d(:,:,:,np1)   [level field]
   double* ps_v;              // out: state%ps_v(:,:,np1)     [e][16]
-  const double* dA;          // [NLEV] (hyai(k+1)-hyai(k))*ps0
-  const double* dB;          // [NLEV] hybi(k+1)-hybi(k)
+  double dA[NLEV];           // (hyai(k+1)-hyai(k))*ps0   (by value: read from the constant bank inside a serial sum)
+  double dB[NLEV];           // hybi(k+1)-hybi(k)
   double hyai0_ps0;          // hyai(1)*ps0
   double dt;
   int Q;
@@ -60,7 +60,7 @@ __device__ __forceinline__ double ppm_dma(double am, double a0, double ap, doubl
   return d;
 }
 
-__global__ void __launch_bounds__(RM_MAX_THREADS, 1) k_vertical_remap(RemapArgs a) {
+__global__ void __launch_bounds__(RM_MAX_THREADS, 1) k_vertical_remap(const __grid_constant__ RemapArgs a) {
   extern __shared__ double sm[];
   const int e = blockIdx.x;
   if (e >= a.nelem) return;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(RM_MAX_THREADS, 1) k_vertical_remap(RemapArgs 
   double* const s_pin = sm + RS_PIN;
   double* const s_g = sm + RS_G;
   unsigned char* const s_kid = reinterpret_cast<unsigned char*>(sm + RS_END);  // [72][16]: kid(k) (1-based cell index)
-  unsigned char* const s_cnt = s_kid + 80 * 16;                                // [74][16]: number of target cells whose kid == j
+  int* const s_cnt = reinterpret_cast<int*>(s_kid + 80 * 16);                  // [74][16]: number of target cells whose kid == j
 
   // ---- grids: everything below is tracer independent -----------------------------------------------------------------
   bool neg = false;
@@ -83,6 +83,11 @@ __global__ void __launch_bounds__(RM_MAX_THREADS, 1) k_vertical_remap(RemapArgs 
     const double d = a.dp[lp] - a.dt * a.divdp_proj[lp];  // dp3d(np1) = dp_star (:1310-1313)
     a.dp3d[lp] = d;
     s_dpo[(k + 2) * 16 + n] = d;
+    // mirrored ghost cells (:147-150): dpo(0) = dpo(1), dpo(-1) = dpo(2), dpo(nlev+1) = dpo(nlev), dpo(nlev+2) = dpo(nlev-1)
+    if (k == 0) s_dpo[1 * 16 + n] = d;
+    if (k == 1) s_dpo[0 * 16 + n] = d;
+    if (k == NLEV - 1) s_dpo[74 * 16 + n] = d;
+    if (k == NLEV - 2) s_dpo[75 * 16 + n] = d;
     neg |= (d < 0.0);
   }
   for (int i = t; i < 74 * 16; i += nthr) s_cnt[i] = 0;
@@ -92,26 +97,22 @@ __global__ void __launch_bounds__(RM_MAX_THREADS, 1) k_vertical_remap(RemapArgs 
     return;
   }
   if (t < 32) {
-    // sequential sums in the reference's order, one lane per column: lanes 0..15 ps_v and pin, lanes 16..31 pio
-    double s = 0.0;
-#pragma unroll 8
-    for (int k = 1; k <= NLEV; ++k) s += s_dpo[(k + 1) * 16 + n];  // sum(dp3d,3); both half-warps, same value
-    const double ps = a.hyai0_ps0 + s;
+    // Sequential sums in the reference's order, one lane per column: lanes 0..15 ps_v and pin, lanes 16..31 pio.  The other
+    // warps compute the PPM grid coefficients meanwhile (they depend on dpo only).
     if (t < 16) {
+      double s = 0.0;
+#pragma unroll 8
+      for (int k = 1; k <= NLEV; ++k) s += s_dpo[(k + 1) * 16 + n];  // sum(dp3d,3)
+      const double ps = a.hyai0_ps0 + s;
       a.ps_v[(size_t)e * 16 + n] = ps;
       double pin = 0.0;
-#pragma unroll 4
+      s_pin[0 * 16 + n] = 0.0;
+#pragma unroll 8
       for (int k = 1; k < NLEV; ++k) {
         pin += a.dA[k - 1] + a.dB[k - 1] * ps;  // dp = dA*ps0 + dB*ps_v (:1314-1316)
         s_pin[k * 16 + n] = pin;                // pin(k+1) at index k
       }
-      s_pin[0 * 16 + n] = 0.0;
-      s_pin[NLEV * 16 + n] = s;  // pin(nlev+1) = pio(nlev+1) (:144): the same sequential sum as pio below
-      // mirrored ghost cells (:147-150)
-      s_dpo[0 * 16 + n] = s_dpo[3 * 16 + n];    // dpo(-1) = dpo(2)
-      s_dpo[1 * 16 + n] = s_dpo[2 * 16 + n];    // dpo(0)  = dpo(1)
-      s_dpo[74 * 16 + n] = s_dpo[73 * 16 + n];  // dpo(nlev+1) = dpo(nlev)
-      s_dpo[75 * 16 + n] = s_dpo[72 * 16 + n];  // dpo(nlev+2) = dpo(nlev-1)
+      s_pin[NLEV * 16 + n] = s;  // pin(nlev+1) = pio(nlev+1) (:144): the same sequential sum as pio
     } else {
       double pio = 0.0;
       s_pio[0 * 16 + n] = 0.0;
@@ -123,36 +124,34 @@ __global__ void __launch_bounds__(RM_MAX_THREADS, 1) k_vertical_remap(RemapArgs 
       s_pio[(NLEV + 1) * 16 + n] = pio + 1.0;  // sentinel (:141)
     }
   }
-  __syncthreads();
-  // compute_ppm_grids (:221-260) for every (level j = 0..73, column); dx(j) = s_dpo[j+1]
-  for (int i = t; i < 74 * 16; i += nthr) {
-    const int j = i >> 4;
-    const double dm = s_dpo[j * 16 + n], d0 = s_dpo[(j + 1) * 16 + n], d1 = s_dpo[(j + 2) * 16 + n];
-    double px0, px1, px2, px3 = 0, px4 = 0, px5 = 0, px8 = 0, px9 = 0;
-    px0 = d0 / (dm + d0 + d1);
-    px1 = (2. * dm + d0) / (d1 + d0);
-    px2 = (d0 + 2. * d1) / (dm + d0);
-    if (j <= NLEV) {
-      const double d2 = s_dpo[(j + 3) * 16 + n];
-      px3 = d0 / (d0 + d1);
-      px4 = 1. / (dm + d0 + d1 + d2);
-      const double p5 = (2. * d1 * d0) / (d0 + d1), p6 = (dm + d0) / (2. * d0 + d1), p7 = (d2 + d1) / (2. * d1 + d0);
-      px5 = p5 * (p6 - p7);  // the reference's dx(6)*(dx(7)-dx(8)) (:303), evaluated once
-      px8 = d0 * (dm + d0) / (2. * d0 + d1);
-      px9 = d1 * (d1 + d2) / (d0 + 2. * d1);
+  // compute_ppm_grids (:221-260) for every (level j = 0..73, column); dx(j) = s_dpo[j+1].  Warp 0 joins after its sums when the
+  // CTA is a single warp.
+  {
+    const int t0 = nthr > 32 ? t - 32 : t, nt = nthr > 32 ? nthr - 32 : nthr;
+    for (int i = t0; i >= 0 && i < 74 * 16; i += nt) {
+      const int j = i >> 4;
+      const double dm = s_dpo[j * 16 + n], d0 = s_dpo[(j + 1) * 16 + n], d1 = s_dpo[(j + 2) * 16 + n];
+      // stage-1 coefficients of level j are used by step j+1 (dma(j)), stage-2 coefficients by step j+2 (ai(j))
+      double* r1 = reinterpret_cast<double*>(s_px + (size_t)(j + 1) * 4 * 16 + n);
+      r1[0] = d0 / (dm + d0 + d1);              // pair 0
+      r1[1] = (2. * dm + d0) / (d1 + d0);
+      r1[32] = (d0 + 2. * d1) / (dm + d0);      // pair 1, first half
+      if (j >= 1 && j <= NLEV) s_rdpo[(j - 1) * 16 + n] = 1.0 / d0;
+      if (j <= NLEV) {
+        const double d2 = s_dpo[(j + 3) * 16 + n];
+        double* r2 = reinterpret_cast<double*>(s_px + (size_t)(j + 2) * 4 * 16 + n);
+        const double r01 = 1.0 / (d0 + d1), r201 = 1.0 / (2. * d0 + d1), r021 = 1.0 / (d0 + 2. * d1);
+        r2[33] = d0 * r01;                        // px3                     pair 1, second half
+        r2[64] = 1. / (dm + d0 + d1 + d2);        // px4                     pair 2
+        // the reference's dx(6)*(dx(7)-dx(8)) (:303), evaluated once.  (Shared reciprocals instead of 6 more divisions: the
+        // coefficients differ from the reference's by <= 2 ulp.)
+        r2[65] = (2. * d1 * d0) * r01 * ((dm + d0) * r201 - (d2 + d1) * r021);
+        r2[96] = d0 * (dm + d0) * r201;           // px8                     pair 3
+        r2[97] = d1 * (d1 + d2) * r021;           // px9
+      }
     }
-    // stage-1 coefficients of level j are used by step j+1 (dma(j)), stage-2 coefficients by step j+2 (ai(j))
-    double* r1 = reinterpret_cast<double*>(s_px + (size_t)(j + 1) * 4 * 16 + n);
-    r1[0] = px0; r1[1] = px1;       // pair 0
-    r1[32] = px2;                   // pair 1, first half
-    if (j <= NLEV) {
-      double* r2 = reinterpret_cast<double*>(s_px + (size_t)(j + 2) * 4 * 16 + n);
-      r2[33] = px3;                 // pair 1, second half
-      r2[64] = px4; r2[65] = px5;   // pair 2
-      r2[96] = px8; r2[97] = px9;   // pair 3
-    }
-    if (j >= 1 && j <= NLEV) s_rdpo[(j - 1) * 16 + n] = 1.0 / d0;
   }
+  __syncthreads();
   // search (:155-173): kid(k) = old cell holding new interface k+1, z2 its normalised position; integration weights of
   // integrate_parabola (:349-356) with x1 = -0.5
   for (int i = t; i < NLEV * 16; i += nthr) {
@@ -164,16 +163,12 @@ __global__ void __launch_bounds__(RM_MAX_THREADS, 1) k_vertical_remap(RemapArgs 
     if (kk == NLEV + 1) kk = NLEV;
     const double dk = s_dpo[(kk + 1) * 16 + n];
     const double x2 = (pk - (s_pio[(kk - 1) * 16 + n] + s_pio[kk * 16 + n]) * 0.5) / dk, x1 = -0.5;
-    s_kid[(k - 1) * 16 + n] = (unsigned char)kk;
+    atomicAdd(s_cnt + kk * 16 + n, 1);  // target cells per source cell (kid is monotone: the emission below is a merge)
     double* g = s_g + (size_t)(k - 1) * 4 * 16 + n;
     g[0] = x2 - x1;
     g[16] = (x2 * x2 - x1 * x1) * 0.5;
     g[32] = (x2 * x2 * x2 - x1 * x1 * x1) / 3.0;
     g[48] = dk;
-  }
-  __syncthreads();
-  if (t < 16) {  // cells per old cell (kid is monotone: a run-length count per column)
-    for (int k = 0; k < NLEV; ++k) s_cnt[s_kid[k * 16 + n] * 16 + n] += 1;
   }
   __syncthreads();
 
@@ -198,8 +193,9 @@ __global__ void __launch_bounds__(RM_MAX_THREADS, 1) k_vertical_remap(RemapArgs 
     double massn1 = 0.0;
     int k = 0;            // next target cell (0-based)
 
-    // one step of the walk: newest source value a3 = ao(j) (raw Qdp `raw`), coefficient row `row` = step j
-    auto step = [&](double raw, double a3, const double2* row, int cnt) {
+    // One step of the walk: newest source value a3 = ao(j), coefficient row = step j.  Produces the parabola of cell j-2
+    // (c0, c1, c2); straight-line code, so that the four steps of a round interleave in the instruction stream.
+    auto step = [&](double raw, double a3, const double2* row, double& c0, double& c1, double& c2, double& mo) {
       const double2 p01 = row[0], p23 = row[16], p45 = row[32], p89 = row[48];
       // dma(j-1) from ao(j-2), ao(j-1), ao(j) and (px0,px1,px2) of level j-1
       const double dma = ppm_dma(a1, a2, a3, p01, p23.x);
@@ -215,17 +211,10 @@ __global__ void __launch_bounds__(RM_MAX_THREADS, 1) k_vertical_remap(RemapArgs 
       // the reference divides by 6 (:323-329); multiplying by the rounded reciprocal differs by <= 1 ulp
       if ((ar - al) * (aj - (al + ar) * 0.5) > (ar - al) * (ar - al) * (1.0 / 6.0)) al = 3. * aj - 2. * ar;
       if ((ar - al) * (aj - (al + ar) * 0.5) < -((ar - al) * (ar - al)) * (1.0 / 6.0)) ar = 3. * aj - 2. * al;
-      const double c0 = 1.5 * aj - (al + ar) * 0.25, c1 = ar - al, c2 = -6. * aj + 3. * (al + ar);
-      // target cells whose lower interface lies in cell j-2: massn2 = masso(kid) + integral*dpo(kid) (:201-209)
-#pragma unroll 1
-      for (; cnt > 0; --cnt) {
-        const double* g = s_g + k * 64 + n;
-        const double integ = c0 * g[0] + c1 * g[16] + c2 * g[32];
-        const double massn2 = masso + integ * g[48];
-        col[(k >> 2) * skc + (k & 3) * 16] = massn2 - massn1;
-        massn1 = massn2;
-        ++k;
-      }
+      c0 = 1.5 * aj - (al + ar) * 0.25;
+      c1 = ar - al;
+      c2 = -6. * aj + 3. * (al + ar);
+      mo = masso;  // masso(j-2)
       masso += r1;
       r1 = r2;
       r2 = raw;
@@ -233,6 +222,18 @@ __global__ void __launch_bounds__(RM_MAX_THREADS, 1) k_vertical_remap(RemapArgs 
       a2 = a3;
       dma_prev = dma;
       ai_prev = ai;
+    };
+    // target cells whose lower interface lies in the cell of this parabola: massn2 = masso(kid) + integral*dpo(kid) (:201-209)
+    auto emit = [&](int cnt, double c0, double c1, double c2, double mo) {
+#pragma unroll 1
+      for (; cnt > 0; --cnt) {
+        const double* g = s_g + k * 64 + n;
+        const double integ = c0 * g[0] + c1 * g[16] + c2 * g[32];
+        const double massn2 = mo + integ * g[48];
+        col[(k >> 2) * skc + (k & 3) * 16] = massn2 - massn1;
+        massn1 = massn2;
+        ++k;
+      }
     };
 
     // steps j = 3 + 4 i + u; source level j sits in chunk (2 + 4 i + u) / 4 at position (2 + u) % 4
@@ -242,23 +243,35 @@ __global__ void __launch_bounds__(RM_MAX_THREADS, 1) k_vertical_remap(RemapArgs 
       const int j = 3 + 4 * i;
       const double2* row = px + j * 64;
       const double* rd = s_rdpo + (j - 1) * 16 + n;
-      const unsigned char* cn = s_cnt + (j - 2) * 16 + n;
-      double raw;
-      raw = ring[0]; ring[0] = src[32];        step(raw, raw * rd[0], row, cn[0]);
-      raw = ring[1]; ring[1] = src[48];        step(raw, raw * rd[16], row + 64, cn[16]);
-      raw = ring[2]; if (i < 16) ring[2] = src[skc];      step(raw, raw * rd[32], row + 128, cn[32]);
-      raw = ring[3]; if (i < 16) ring[3] = src[skc + 16]; step(raw, raw * rd[48], row + 192, cn[48]);
+      const int* cn = s_cnt + (j - 2) * 16 + n;
+      const double w0 = ring[0], w1 = ring[1], w2 = ring[2], w3 = ring[3];
+      ring[0] = src[32];
+      ring[1] = src[48];
+      if (i < 16) {
+        ring[2] = src[skc];
+        ring[3] = src[skc + 16];
+      }
+      double c[4][3], mo[4];
+      step(w0, w0 * rd[0], row, c[0][0], c[0][1], c[0][2], mo[0]);
+      step(w1, w1 * rd[16], row + 64, c[1][0], c[1][1], c[1][2], mo[1]);
+      step(w2, w2 * rd[32], row + 128, c[2][0], c[2][1], c[2][2], mo[2]);
+      step(w3, w3 * rd[48], row + 192, c[3][0], c[3][1], c[3][2], mo[3]);
+      TSE_UNROLL
+      for (int u = 0; u < 4; ++u) emit(cn[16 * u], c[u][0], c[u][1], c[u][2], mo[u]);
       src += skc;
     }
     {  // last round, j = 71..74: two real levels, then the mirrored cells ao(73) = ao(72), ao(74) = ao(71)
       const double2* row = px + 71 * 64;
       const double* rd = s_rdpo + 70 * 16 + n;
-      const unsigned char* cn = s_cnt + 69 * 16 + n;
-      step(ring[0], ring[0] * rd[0], row, cn[0]);
-      step(ring[1], ring[1] * rd[16], row + 64, cn[16]);
+      const int* cn = s_cnt + 69 * 16 + n;
+      double c[4][3], mo[4];
+      step(ring[0], ring[0] * rd[0], row, c[0][0], c[0][1], c[0][2], mo[0]);
+      step(ring[1], ring[1] * rd[16], row + 64, c[1][0], c[1][1], c[1][2], mo[1]);
       const double a71 = a1;                    // at the top of step 73: a1 = ao(71), a2 = ao(72)
-      step(0.0, a2, row + 128, cn[32]);
-      step(0.0, a71, row + 192, cn[48]);
+      step(0.0, a2, row + 128, c[2][0], c[2][1], c[2][2], mo[2]);
+      step(0.0, a71, row + 192, c[3][0], c[3][1], c[3][2], mo[3]);
+      TSE_UNROLL
+      for (int u = 0; u < 4; ++u) emit(cn[16 * u], c[u][0], c[u][1], c[u][2], mo[u]);
     }
   }
 }

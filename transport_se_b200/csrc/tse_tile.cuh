@@ -44,7 +44,7 @@ static_assert(EPW > 1 || (TT / 8) % GPL == 0 || GPL % (TT / 8) == 0, "swizzle");
 // (lanes 0..7 = 4 levels x 2 elements for EPW > 1, 4 levels x 2 tracers for EPW == 1)
 __host__ __device__ constexpr int swz(int p) { return EPW > 1 ? (p & 7) : ((p & 3) | (((p / GPL) & 1) << 2)); }
 
-enum TileOp { OP_MINMAX = 0, OP_STAGE1, OP_STAGE2, OP_STAGE3, OP_BIHARM_PRE, OP_TIME_AVG, OP_RESOLVE };
+enum TileOp { OP_MINMAX = 0, OP_STAGE1, OP_STAGE2, OP_STAGE3, OP_BIHARM_PRE, OP_TIME_AVG, OP_RESOLVE, OP_MASS };
 
 struct TileTables {
   const int* gsrc_t;    // [npad][NSLOT]: <0 none, [0,256) in-group (el<<4|node), >=256 halo entry (code-256)
@@ -65,6 +65,10 @@ struct TileArgs {
   int Q;
   int store_bounds;  // stage ops: write the limiter's relaxed qmin/qmax back (needed after stage 1; otherwise only for inspection)
   int zero;          // always 0 (a value the compiler cannot fold: see mbar_arrive_after in tse_pipe.cuh)
+  // OP_MASS (tse_diag_mass): fixed-point accumulators [2*Q], running max of |J| as bits [Q], binary shift per tracer [Q]
+  long long* mass_acc;
+  unsigned long long* mass_maxbits;
+  const int* mass_shift;
   const int* glist;  // optional list of groups this launch covers (boundary groups first, interior groups while the halo is in flight)
 };
 
@@ -83,7 +87,8 @@ __host__ __device__ constexpr TileCfg tile_cfg(int op) {
        : op == OP_STAGE3 ? TileCfg{4, 6, 1, 0, 1, 2, -1, 3, 0, 1, 2, 3, 4, 5}
        : op == OP_MINMAX ? TileCfg{1, 0, 0, -1, -1, -1, 0, -1, -1, -1, -1, -1, -1, -1}
        : op == OP_BIHARM_PRE ? TileCfg{1, 3, 1, -1, -1, -1, 0, -1, -1, -1, -1, 0, 1, 2}
-                             : TileCfg{0, 1, 1, -1, -1, -1, -1, -1, -1, -1, 0, -1, -1, -1};
+       : op == OP_MASS ? TileCfg{0, 2, 0, -1, -1, -1, -1, -1, 0, -1, 1, -1, -1, -1}   // E1 slot = spheremp (unscaled), RSPH
+                       : TileCfg{0, 1, 1, -1, -1, -1, -1, -1, -1, -1, 0, -1, -1, -1};
 }
 // one IN stage: tile, halo [tracer][halo node][level], a zero (target of absent DSS neighbours), limiter bounds qmin|qmax [tracer][plane]
 constexpr int BND_BYTES = 2 * QI * GPL * 8;
@@ -393,54 +398,112 @@ __device__ __forceinline__ void laplace_wk_el(const double (&s)[16], const Dvv& 
   }
 }
 
-// min/max over the element and its up to 8 neighbours (neighbor_minmax, viscosity_mod.F90:748-816).  One thread per (element,
-// level chunk, tracer): the KC = 4 levels of a chunk are contiguous (32 bytes = one sector) both in the per-plane extrema
-// arrays and in the ghost bundles, so every neighbour costs two 16-byte loads per array instead of four 8-byte ones.
-static_assert(KC == 4 && NLEV % KC == 0, "k_nbr_minmax reads the 4 levels of a chunk as two double2");
-__global__ void __launch_bounds__(256) k_nbr_minmax(Geo G, int Q, const double* __restrict__ lmin, const double* __restrict__ lmax,
-                                                    const double* __restrict__ ghost_mm, double* __restrict__ qmin,
-                                                    double* __restrict__ qmax) {
-  const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // index of (g, kc, q, el) in layout order
-  const size_t total = (size_t)G.ngroups * NKC * Q * GE;
-  if (r >= total) return;
-  const int el = r % GE;
-  const size_t r2 = r / GE;
-  const int q = r2 % Q;
-  const size_t gk = r2 / Q;
-  const int kc = gk % NKC, g = gk / NKC;
+// min/max over the element and its up to 8 neighbours (neighbor_minmax, viscosity_mod.F90:748-816).
+// CTA = (group, level chunk), walking the tracers two at a time.  The element extrema of the group (2 x 512 contiguous bytes per
+// tracer) and of the neighbour elements outside the group (one 32-byte sector each: the KC = 4 levels of a chunk are contiguous
+// both in the per-plane arrays and in the ghost bundles) are staged in shared memory with 16-byte loads; each thread then forms
+// the 9-way min/max of one (element, level) from shared memory.  The plane-per-thread version read every neighbour straight
+// from global memory, 18 sector requests per plane, and ran into the L1 wavefront limit (92 % of the LSU data pipe, 0.36 of the
+// HBM roofline); here a sector is requested once per group.
+struct NbrTables {
+  const int* nbr_t;    // [npad][8]: < 0 none, [0, GE) element of the same group, >= 256: external entry (code - 256) of the group
+  const int* ext_off;  // [ngroups + 1]
+  const int* ext_src;  // [ext_off[ngroups]]: >= 0 element (internal order), <= -2 ghost bundle -(v + 2)
+  int xmax;            // max external entries of a group
+};
+constexpr int NBQ = 2;  // tracers per batch = NBQ * GPL threads
+__host__ __device__ constexpr int nbr_smem_bytes(int xmax) { return 2 * 2 * NBQ * (GPL + xmax * KC) * 8; }
+static_assert(KC == 4 && NLEV % KC == 0, "k_nbr_minmax moves the 4 levels of a chunk as two double2");
+
+__global__ void __launch_bounds__(NBQ* GPL) k_nbr_minmax(Geo G, NbrTables nt, int Q, const double* __restrict__ lmin,
+                                                        const double* __restrict__ lmax, const double* __restrict__ ghost_mm,
+                                                        double* __restrict__ qmin, double* __restrict__ qmax) {
+  extern __shared__ double nsm[];  // [buf 2][arr 2][q NBQ][GPL + xmax*KC]
+  const int t = threadIdx.x;
+  const int ngl = gridDim.x / NKC;
+  const int g = blockIdx.x % ngl, kc = blockIdx.x / ngl;  // chunk-major like k_pipe: neighbouring groups run together (L2)
+  const int W = GPL + nt.xmax * KC;                        // scalars per (array, tracer) in shared memory
+  const int xo = nt.ext_off[g], nx = nt.ext_off[g + 1] - xo;
+  const size_t tile0 = (((size_t)g * NKC + kc) * Q) * GPL;  // plane index of (tracer 0, plane 0) of this CTA
+
+  // loader role.  Own tiles: NBQ*2 arrays x GPL scalars = one double2 per thread.  External sectors: item = (q, arr, x, half).
+  const int own_arr = (t / (GPL / 2)) & 1, own_q = t / GPL, own_h = t % (GPL / 2);
+  constexpr int XI = 2;  // external items per thread (covers xmax <= 32 with NBQ*GPL = 128 threads; more loop below)
+  // consumer role: one (tracer, element, level) per thread
+  const int cq = t / GPL, pl = t % GPL, el = pl / KC, kk = pl % KC;
   const int e = g * GE + el;
-  if (e >= G.nelem) return;
-  const double2* mn2 = reinterpret_cast<const double2*>(lmin + r * KC);
-  const double2* mx2 = reinterpret_cast<const double2*>(lmax + r * KC);
-  double2 mna = mn2[0], mnb = mn2[1], mxa = mx2[0], mxb = mx2[1];
-  const int4* nb4 = reinterpret_cast<const int4*>(G.nbr8 + (size_t)e * 8);
-  const int4 n0 = nb4[0], n1 = nb4[1];
-  const int nb[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
-  // branch-free: an absent neighbour reads the element itself (min/max with itself changes nothing), so that all 32 loads are
-  // independent and go out together -- the kernel is latency bound
-  const double2 *pn[8], *px[8];
-  TSE_UNROLL
-  for (int d = 0; d < 8; ++d) {
-    const int b = nb[d];
-    const size_t pb = b >= 0 ? qplane(b, q, kc * KC, Q) : r * KC;
-    const size_t gb = ((size_t)(b <= -2 ? -b - 2 : 0) * 2 * Q + q) * NLEV + kc * KC;
-    pn[d] = reinterpret_cast<const double2*>(b <= -2 ? ghost_mm + gb : lmin + pb);
-    px[d] = reinterpret_cast<const double2*>(b <= -2 ? ghost_mm + gb + (size_t)Q * NLEV : lmax + pb);
+  int noff[8];
+  {
+    const int4* n4 = reinterpret_cast<const int4*>(nt.nbr_t + (size_t)min(e, G.nelem - 1) * 8);
+    const int4 u = n4[0], v = n4[1];
+    const int c[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+    TSE_UNROLL
+    for (int d = 0; d < 8; ++d) noff[d] = c[d] < 0 ? pl : c[d] >= 256 ? GPL + (c[d] - 256) * KC + kk : c[d] * KC + kk;
   }
-  double2 va[8][4];
+  const int nitems = 2 * 2 * NBQ * nx;  // (half, x, arr, q)
+  // decode an external item once: source of tracer slot 0 .. NBQ-1 of batch 0 (pointer to tracer ql, stride per tracer) and
+  // the destination in a shared-memory buffer
+  auto ext_decode = [&](int it, const double*& base, int& stride, int& ql, int& dst) {
+    const int half = it & 1, idx = it >> 1, x = idx % nx, r = idx / nx, arr = r & 1;
+    ql = r >> 1;
+    const int src = nt.ext_src[xo + x];
+    if (src >= 0) {
+      base = (arr ? lmax : lmin) + qplane(src, 0, kc * KC, Q) + 2 * half;
+      stride = GPL;
+    } else {
+      base = ghost_mm + ((size_t)(-src - 2) * 2 + arr) * Q * NLEV + kc * KC + 2 * half;
+      stride = NLEV;
+    }
+    dst = (arr * NBQ + ql) * W + GPL + x * KC + 2 * half;
+  };
+  const double* e_base[XI];
+  int e_stride[XI], e_ql[XI], e_dst[XI];
   TSE_UNROLL
-  for (int d = 0; d < 8; ++d) {
-    va[d][0] = pn[d][0]; va[d][1] = pn[d][1]; va[d][2] = px[d][0]; va[d][3] = px[d][1];
+  for (int i = 0; i < XI; ++i) {
+    e_base[i] = lmin; e_stride[i] = 0; e_ql[i] = 0; e_dst[i] = 0;
+    const int it = t + i * NBQ * GPL;
+    if (it < nitems) ext_decode(it, e_base[i], e_stride[i], e_ql[i], e_dst[i]);
   }
-  TSE_UNROLL
-  for (int d = 0; d < 8; ++d) {
-    mna.x = dmin(mna.x, va[d][0].x); mna.y = dmin(mna.y, va[d][0].y); mnb.x = dmin(mnb.x, va[d][1].x); mnb.y = dmin(mnb.y, va[d][1].y);
-    mxa.x = dmax(mxa.x, va[d][2].x); mxa.y = dmax(mxa.y, va[d][2].y); mxb.x = dmax(mxb.x, va[d][3].x); mxb.y = dmax(mxb.y, va[d][3].y);
+  const double* const own_base = (own_arr ? lmax : lmin) + tile0 + 2 * own_h;
+  const int nb = (Q + NBQ - 1) / NBQ;
+  double2 r_own, r_ext[XI];
+  auto prefetch = [&](int b) {
+    const int q0 = b * NBQ;
+    r_own = *reinterpret_cast<const double2*>(own_base + (size_t)min(q0 + own_q, Q - 1) * GPL);
+    TSE_UNROLL
+    for (int i = 0; i < XI; ++i)
+      if (t + i * NBQ * GPL < nitems) r_ext[i] = *reinterpret_cast<const double2*>(e_base[i] + (size_t)min(q0 + e_ql[i], Q - 1) * e_stride[i]);
+  };
+  prefetch(0);
+  for (int b = 0; b < nb; ++b) {
+    double* sb = nsm + (size_t)(b & 1) * 2 * NBQ * W;
+    *reinterpret_cast<double2*>(sb + (own_arr * NBQ + own_q) * W + 2 * own_h) = r_own;
+    TSE_UNROLL
+    for (int i = 0; i < XI; ++i)
+      if (t + i * NBQ * GPL < nitems) *reinterpret_cast<double2*>(sb + e_dst[i]) = r_ext[i];
+    for (int it = t + XI * NBQ * GPL; it < nitems; it += NBQ * GPL) {  // groups with more than 32 external neighbours
+      const double* base;
+      int stride, ql, dst;
+      ext_decode(it, base, stride, ql, dst);
+      *reinterpret_cast<double2*>(sb + dst) = *reinterpret_cast<const double2*>(base + (size_t)min(b * NBQ + ql, Q - 1) * stride);
+    }
+    __syncthreads();
+    if (b + 1 < nb) prefetch(b + 1);
+    const int q = b * NBQ + cq;
+    const double* smn = sb + cq * W;
+    const double* smx = sb + (NBQ + cq) * W;
+    double mn = smn[pl], mx = smx[pl];
+    TSE_UNROLL
+    for (int d = 0; d < 8; ++d) {
+      mn = dmin(mn, smn[noff[d]]);
+      mx = dmax(mx, smx[noff[d]]);
+    }
+    if (q < Q && e < G.nelem) {
+      const size_t pidx = tile0 + (size_t)q * GPL + pl;
+      qmin[pidx] = mn;
+      qmax[pidx] = mx;
+    }
   }
-  double2* on = reinterpret_cast<double2*>(qmin + r * KC);
-  double2* ox = reinterpret_cast<double2*>(qmax + r * KC);
-  on[0] = mna; on[1] = mnb;
-  ox[0] = mxa; ox[1] = mxb;
 }
 
 }  // namespace tse
