@@ -151,10 +151,9 @@ __device__ __forceinline__ unsigned any_outside(const double (&x)[16], double lo
 // bound -minp for the downward case (negation is exact) leaves one code path, whose sweep fuses "add the increment"
 // (:1052-1078 of sweep i), "clip" (:1037-1045 of sweep i+1) and the next weightssum; the weight of a node is carried in a
 // register and zeroed when the node reaches the bound, which removes the per-node "still below the bound?" tests.
-__device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsigned rcbase, double sumc, double& minp, double& maxp) {
-  const double tol_limiter = (double)5e-14f;
-  if (sumc <= 0.0) return;
-  double mass;
+// limiter_check: mass, relaxation of the bounds, and the test "does any node leave [minp, maxp]".  Returns 1 if the slow path has
+// to run (y is untouched either way).  Requires sumc > 0.
+__device__ __forceinline__ unsigned limiter_check(const double (&y)[16], unsigned rcbase, double sumc, double& minp, double& maxp, double& mass) {
   {
     double m0 = y[0], m1 = y[1], m2 = y[2], m3 = y[3];
     TSE_UNROLL
@@ -169,19 +168,19 @@ __device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsig
   if (mass < minp * sumc) minp = mass / sumc;
   if (mass > maxp * sumc) maxp = mass / sumc;
   // any x = y*rc outside [minp, maxp]?  (DMUL + 2 DSETP per node)
-  unsigned viol;
-  {
-    double x[16];
-    TSE_UNROLL
-    for (int cc = 0; cc < 8; ++cc) {
-      const double2 r = lds128v(rcbase + cc * GPL * 16);
-      x[2 * cc] = y[2 * cc] * r.x;
-      x[2 * cc + 1] = y[2 * cc + 1] * r.y;
-    }
-    viol = any_outside(x, minp, maxp);
+  double x[16];
+  TSE_UNROLL
+  for (int cc = 0; cc < 8; ++cc) {
+    const double2 r = lds128v(rcbase + cc * GPL * 16);
+    x[2 * cc] = y[2 * cc] * r.x;
+    x[2 * cc + 1] = y[2 * cc + 1] * r.y;
   }
-  if (!viol) return;
+  return any_outside(x, minp, maxp);
+}
 
+// limiter_slow: the clip / redistribute sweeps, for a plane limiter_check flagged (minp/maxp already relaxed, mass from the check).
+__device__ __forceinline__ void limiter_slow(double (&y)[16], unsigned cbase, unsigned rcbase, double mass, double minp, double maxp) {
+  const double tol_limiter = (double)5e-14f;
   // ---- slow path ---------------------------------------------------------------------------------------------------
   // x = y*rc in place of y.  Sweep 1 clips against both bounds (:1037-1045).
   const double thresh = tol_limiter * fabs(mass);
@@ -282,6 +281,13 @@ __device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsig
     y[2 * cc] *= c.x;
     y[2 * cc + 1] *= c.y;
   }
+}
+
+// the whole limiter on one plane (check, then the sweeps if needed)
+__device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsigned rcbase, double sumc, double& minp, double& maxp) {
+  if (sumc <= 0.0) return;  // (:1016)
+  double mass;
+  if (limiter_check(y, rcbase, sumc, minp, maxp, mass)) limiter_slow(y, cbase, rcbase, mass, minp, maxp);
 }
 
 // Verification hook (tse_debug_limiter): the limiter exactly as the stage kernels call it -- c and 1/c staged in shared memory in
