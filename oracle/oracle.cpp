@@ -27,6 +27,9 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace {
 
@@ -1047,6 +1050,17 @@ void* orc_create(int nelem, int qsize, int nlev, const double* dvv, const double
   return o;
 }
 void orc_destroy(void* h) { delete (Oracle*)h; }
+// thread count of the element loops (the reference's HORIZ_OPENMP decomposition); returns the count in effect.  Launchers such
+// as torchrun export OMP_NUM_THREADS=1: a timing harness has to set the count itself.
+int orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
 
 // raw pointer to a named field (numpy views it); *count = number of doubles
 double* orc_field(void* h, const char* name, long long* count) {

@@ -31,6 +31,8 @@ def lib():
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_int, C.c_int, C.c_int] + [_dp] * 8 + [_ip] * 3 + [C.c_int] + [_dp] * 4 + [C.c_double, C.c_int]
         L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_set_num_threads.restype = C.c_int
         L.orc_field.restype = _dp
         L.orc_field.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_longlong)]
         L.orc_get_tl.argtypes = [C.c_void_p, _ip]
@@ -60,6 +62,11 @@ def lib():
         L.orc_dcmip_point.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _dp]
         _LIB = L
     return _LIB
+
+
+def set_num_threads(n):
+    """OpenMP threads of the oracle's element loops; returns the count in effect (n <= 0: just query)."""
+    return lib().orc_set_num_threads(int(n))
 
 
 class Oracle:
