@@ -61,3 +61,25 @@ def build_oracle(force=False):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         _run(["g++", "-O3", "-march=x86-64-v3", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-o", out, src])
     return out
+
+
+def build_driver(force=False):
+    """driver/prim_main: the C++ stand-alone driver (namelist, time loop, printstate, error norms) linked against libtse_cuda.so."""
+    out = os.path.join(ROOT, "driver", "prim_main")
+    srcs = [os.path.join(ROOT, "driver", "prim_main.cpp"), os.path.join(CSRC, "tse_mesh.cpp")]
+    deps = srcs + [os.path.join(CSRC, "tse_mesh.hpp"), os.path.join(ROOT, "include", "tse.h"), os.path.join(_HERE, "libtse_cuda.so")]
+    if force or _newer(out, deps):
+        _run(["g++", "-O2", "-std=gnu++17", "-fopenmp", "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", out] + srcs +
+             ["-L", _HERE, "-ltse_cuda", "-lquadmath", "-Wl,-rpath," + _HERE, "-Wl,--allow-shlib-undefined"])
+    return out
+
+
+def build_c_abi_check(force=False):
+    """tests/c_abi/abi_check: a C11 program that includes include/tse.h and drives the library without ctypes."""
+    out = os.path.join(ROOT, "tests", "c_abi", "abi_check")
+    src = os.path.join(ROOT, "tests", "c_abi", "abi_check.c")
+    deps = [src, os.path.join(ROOT, "include", "tse.h"), os.path.join(_HERE, "libtse_cuda.so"), os.path.join(_HERE, "libtse_host.so")]
+    if force or _newer(out, deps):
+        _run(["gcc", "-O1", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", out, src,
+              "-L", _HERE, "-ltse_cuda", "-ltse_host", "-lm", "-Wl,-rpath," + _HERE, "-Wl,--allow-shlib-undefined"])
+    return out
