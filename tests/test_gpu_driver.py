@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import make_oracle, oracle_begin_step, per_tracer_relerr, relerr, TSTEP
+from helpers import make_oracle, oracle_begin_step, oracle_time_update, per_tracer_relerr, relerr, TSTEP
 from transport_se_b200.mesh import Mesh, load_vcoord
 
 pytestmark = pytest.mark.gpu
@@ -104,9 +104,61 @@ def test_config_errors(built):
     from transport_se_b200.advection import TracerAdvection, TseError
     m, v, hv, o = make_oracle(4, 2, 11)
     with pytest.raises(TseError):
-        TracerAdvection(m, v, hv, qsize=2, limiter_option=4)      # cuda_mod.F90:513-517 stops too
-    with pytest.raises(TseError):
-        TracerAdvection(m, v, hv, qsize=2, hypervis_subcycle_q=2)  # namelist_mod.F90:688-692
+        TracerAdvection(m, v, hv, qsize=2, hypervis_subcycle_q=2)  # limiter 8 requires hypervis_subcycle_q=1 (namelist_mod.F90:688-692)
+    # any other limiter_option advects without a limiter, with any hypervis_subcycle_q (read but unused on the reference's CPU path)
+    TracerAdvection(m, v, hv, qsize=2, limiter_option=0, hypervis_subcycle_q=3).close()
+    TracerAdvection(m, v, hv, qsize=2, limiter_option=4).close()
+
+
+@pytest.mark.parametrize("limiter_option", [0, 4])
+def test_other_limiter_options_match_oracle(built, limiter_option):
+    """limiter_option != 8: euler_step without a limiter (prim_advection_mod.F90:858,880 test for 8 only), stage-3 hyperviscosity
+    included; one remap cycle through the fused entry and, for the extrema, one step through the stage-by-stage entry."""
+    from oracle.oracle_lib import DSSeta, DSSomega, DSSdiv_vdp_ave
+    from transport_se_b200.advection import TracerAdvection
+    ne, qsize, test = 8, 5, 11
+    tstep = TSTEP[ne]
+    m, v, hv, o = make_oracle(ne, qsize, test)
+    o.set_params(6e16, 3, limiter_option, test)
+    adv = TracerAdvection(m, v, hv, qsize=qsize, nu_q=6e16, limiter_option=limiter_option)
+    adv.copy_qdp_h2d(o.Qdp, 1)
+    adv.copy_qdp_h2d(o.Qdp, 2)
+    got = np.zeros_like(o.Qdp)
+    # stage by stage: fields and the (unused, but computed by the reference) qmin/qmax
+    oracle_begin_step(o, test, tstep)
+    adv.set_derived(o.vn0, o.dp, o.eta_dot_dpdn, o.omega_p)
+    n0, np1 = o.qdp_levels()
+    o.precompute_divdp()
+    adv.precompute_divdp()
+    for rhs, dss, a, b in ((0, DSSdiv_vdp_ave, np1, n0), (1, DSSeta, np1, np1), (2, DSSomega, np1, np1)):
+        o.euler_step(a, b, tstep / 2, dss, rhs)
+        adv.euler_step(a, b, tstep / 2, dss, rhs)
+        adv.copy_qdp_d2h(got, np1)
+        assert per_tracer_relerr(got[:, np1 - 1], o.Qdp[:, np1 - 1]).max() < 1e-12
+        qmin, qmax = adv.get_qminmax()
+        assert relerr(qmin, o.qmin) < 1e-12 and relerr(qmax, o.qmax) < 1e-12
+    o.qdp_time_avg(3, n0, np1)
+    adv.qdp_time_avg(3, n0, np1)
+    # the unlimited scheme really differs from limiter 8 here (otherwise this test would not see the option)
+    _, _, _, o8 = make_oracle(ne, qsize, test)
+    oracle_begin_step(o8, test, tstep)
+    o8.advec_tracers_remap_rk2(tstep)
+    assert per_tracer_relerr(o.Qdp[:, np1 - 1], o8.Qdp[:, np1 - 1]).max() > 1e-6
+    # two more steps + remap through the fused entry
+    for r in range(1, 3):
+        oracle_time_update(o)
+        oracle_begin_step(o, test, tstep)
+        adv.set_derived(o.vn0, o.dp, o.eta_dot_dpdn, o.omega_p)
+        o.advec_tracers_remap_rk2(tstep)
+        adv.prim_advec_tracers_remap_rk2(tstep, o.tl["nstep"])
+    n0, np1 = o.qdp_levels()
+    assert o.vertical_remap(3 * tstep, o.tl["np1"], np1) == 0
+    adv.vertical_remap(3 * tstep, o.tl["np1"], np1)
+    adv.copy_qdp_d2h(got, np1)
+    err = per_tracer_relerr(got[:, np1 - 1], o.Qdp[:, np1 - 1])
+    print("limiter_option", limiter_option, "relerr after one remap cycle", err)
+    assert err.max() < 5e-12
+    adv.close()
 
 
 @pytest.mark.parametrize("ne,test,cycles,gold", [

@@ -347,6 +347,7 @@ TileArgs tile_args(const tse_state* s) {
   a.Q = s->Q;
   a.rkstage = 3.0;
   a.store_bounds = 1;
+  a.limiter8 = s->cfg.limiter_option == 8 ? 1 : 0;
   return a;
 }
 void set_src(const tse_state* s, TileArgs& a, int i, int buf, int pending) {
@@ -445,8 +446,11 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
              tse_handle* out) {
   if (!cfg || !geom || !conn || !hv || !dvv || !out) return fail("tse_init: null argument");
   if (cfg->np != NP || cfg->nlev != NLEV) return fail("tse_init: built for np=4, nlev=72 (got np=%d nlev=%d)", cfg->np, cfg->nlev);
-  if (cfg->limiter_option != 8) return fail("tse_init: only limiter_option=8 is implemented (got %d)", cfg->limiter_option);
-  if (cfg->hypervis_subcycle_q != 1) return fail("tse_init: limiter 8 requires hypervis_subcycle_q=1 (namelist_mod.F90:688-692)");
+  // limiter_option: 8 = limiter_optim_iter_full; any other value advects without a limiter, exactly like the reference's CPU
+  // path (prim_advection_mod.F90:858,880 test for 8 only; limiter2d_zero / limiter2d_minmax are never called there).
+  // hypervis_subcycle_q is read, broadcast and printed by the reference but used nowhere on its CPU path; the one rule is kept:
+  if (cfg->limiter_option == 8 && cfg->hypervis_subcycle_q != 1)
+    return fail("tse_init: limiter 8 requires hypervis_subcycle_q=1 (namelist_mod.F90:688-692)");
   if (cfg->vert_remap_q_alg == 2) return fail("tse_init: vert_remap_q_alg=2 is not implemented");
   if (cfg->qsize < 1 || cfg->qsize > cfg->qsize_d) return fail("tse_init: qsize=%d qsize_d=%d", cfg->qsize, cfg->qsize_d);
   if (cfg->nelemd < 1) return fail("tse_init: nelemd=%d", cfg->nelemd);
@@ -1033,8 +1037,10 @@ int tse_euler_step(tse_handle s, int np1_qdp, int n0_qdp, double dt, int DSSopt,
   a.store_bounds = (rhs_multiplier == 0 || !s->fused_step) ? 1 : 0;
   int tmp = -1;
   if (wait_halo(s)) return 1;
-  if (rhs_multiplier == 0) {
-    // qmin/qmax = element extrema of Q = Qdp/dp, then min/max over the 8 neighbours (:764-778)
+  if (rhs_multiplier == 0 && (a.limiter8 || !s->fused_step)) {
+    // qmin/qmax = element extrema of Q = Qdp/dp, then min/max over the 8 neighbours (:764-778).  Without limiter 8 nothing reads
+    // them (the reference computes them all the same): the fused driver skips the pass, the stage-by-stage entry keeps it so
+    // that tse_get_qminmax returns what the reference holds.
     set_src(s, a, 0, in, in_pending);
     if (launch_tile_overlapped<OP_MINMAX>(s, a, [&]() { return pack_minmax(s) || exchange(s, {xfer_minmax(s)}); })) return 1;
     if (neighbor_minmax(s)) return 1;

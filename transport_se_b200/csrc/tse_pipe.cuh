@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
 #ifndef TSE_SKIP_LIMITER
         const unsigned cl_a = smem_u32 + (unsigned)(pp - smem) + (cfg.CL < 0 ? 0 : cfg.CL) * PP_BYTES + pl * 16;
         const unsigned rc_a = smem_u32 + (unsigned)(pp - smem) + (cfg.RC < 0 ? 0 : cfg.RC) * PP_BYTES + pl * 16;
-        limiter_y(y, cl_a, rc_a, sumc, minp, maxp);
+        if (a.limiter8) limiter_y(y, cl_a, rc_a, sumc, minp, maxp);  // (:880: only option 8 limits inside euler_step)
 #endif
         asm volatile("" ::: "memory");
         if (a.store_bounds) {  // the relaxed bounds (:1024-1029) are only read again by stage 2 (and by tse_get_qminmax)

@@ -63,6 +63,7 @@ struct TileArgs {
   const double* dp0;
   double *qmin, *qmax, *qmin_loc, *qmax_loc;
   int Q;
+  int limiter8;      // 1: limiter_option == 8 (limiter_optim_iter_full); 0: no limiter inside euler_step, as the reference for every other value
   int store_bounds;  // stage ops: write the limiter's relaxed qmin/qmax back (needed after stage 1; otherwise only for inspection)
   int zero;          // always 0 (a value the compiler cannot fold: see mbar_arrive_after in tse_pipe.cuh)
   // OP_MASS (tse_diag_mass): fixed-point accumulators [2*Q], running max of |J| as bits [Q], binary shift per tracer [Q]
