@@ -26,7 +26,13 @@ namespace tse {
 // CTA moves 32 KB per release -> refill round trip (about 2 us), i.e. 4.7 TB/s over the chip; they get 3-4 stages and, where
 // it still leaves 2 CTAs per SM (113 KB each), a double-buffered OUT tile.  The stage ops carry a 40 KB package: 2 + 1.
 // (OP_MINMAX measured slower with 4 stages than with 2.)
-__host__ __device__ constexpr int pipe_nst(int op) { return (op == OP_BIHARM_PRE || op == OP_TIME_AVG || op == OP_RESOLVE || op == OP_MASS) ? 3 : 2; }
+#ifndef TSE_BIHARM3
+#define TSE_BIHARM3 0  // experiment: OP_BIHARM_PRE with 2 stages and 3 CTAs per SM (112 registers)
+#endif
+__host__ __device__ constexpr int pipe_nst(int op) {
+  return (op == OP_BIHARM_PRE && TSE_BIHARM3) ? 2 : (op == OP_BIHARM_PRE || op == OP_TIME_AVG || op == OP_RESOLVE || op == OP_MASS) ? 3 : 2;
+}
+__host__ __device__ constexpr int pipe_minb(int op) { return (op == OP_BIHARM_PRE && TSE_BIHARM3) ? 3 : TSE_MINB; }
 __host__ __device__ constexpr int pipe_nout(int op) { return (op == OP_TIME_AVG || op == OP_RESOLVE) ? 2 : 1; }
 constexpr int NST_MAX = 4;               // barrier slots reserved per kind
 // Stage release protocol (consumer -> producer, "this stage may be refilled"):
@@ -143,7 +149,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;\n" ::"n"(TT) : "memory"); }
 
 template <int OP>
-__global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 : TSE_MINB)) k_pipe(const __grid_constant__ PipeMaps maps, Geo G, Dvv D, TileTables tb, TileArgs a) {
+__global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 : pipe_minb(OP))) k_pipe(const __grid_constant__ PipeMaps maps, Geo G, Dvv D, TileTables tb, TileArgs a) {
   constexpr TileCfg cfg = tile_cfg(OP);
   constexpr bool kStage = (OP == OP_STAGE1 || OP == OP_STAGE2 || OP == OP_STAGE3);
   constexpr int NIN = (OP == OP_STAGE3 || OP == OP_TIME_AVG) ? 2 : 1;
