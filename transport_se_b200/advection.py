@@ -51,10 +51,28 @@ EXPORTS = ["tse_last_error", "tse_device_count", "tse_init", "tse_finalize", "ts
            "tse_debug_limiter", "tse_diag_field_hash"]
 
 
+def _preload_bundled_nccl():
+    """libtse_cuda.so needs libnccl.so.2.  When this process also uses PyTorch (the harness does, for torch.distributed), the
+    NCCL that gets loaded first wins for both; PyTorch needs the newer one it ships (nvidia/nccl/lib).  Load that one first if it
+    is there, so that the order in which a test imports torch and this module does not matter.  Stand-alone C / Fortran hosts
+    simply use the system library."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            path = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
+
+
 def cuda_lib():
     """Load libtse_cuda.so (built in-tree by transport_se_b200._build.build_cuda / __graft_entry__.build)."""
     global _LIB
     if _LIB is None:
+        _preload_bundled_nccl()
         path = os.environ.get("TSE_CUDA_LIB") or os.path.join(_HERE, "libtse_cuda.so")  # override: kernel-variant experiments (tools/)
         if not os.path.exists(path):
             raise RuntimeError("libtse_cuda.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback)")
