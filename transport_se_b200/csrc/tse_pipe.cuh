@@ -243,8 +243,11 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
     if (any_pending) {
       const int hoff = tb.halo_off[g], H = tb.halo_off[g + 1] - hoff;
       nhalo = H * KC;
-      for (int idx = lane + 32 * pw; idx < nhalo; idx += 32 * NPW) {  // entry idx -> (h = idx % H, kk2 = idx / H), h fastest
-        const int h = idx % H, kk2 = idx / H;
+      // entry idx -> (h = idx / KC, kk2 = idx % KC), level fastest: consecutive lanes then write consecutive 8-byte slots of the
+      // halo array (with the halo node fastest they were 32 bytes apart: 8-way bank conflicts, 11 wavefronts per LDGSTS, 10-18 % of
+      // the shared-memory wavefronts of the ops that gather) and read the 4 levels of one node, 4 sectors of consecutive lines
+      for (int idx = lane + 32 * pw; idx < nhalo; idx += 32 * NPW) {
+        const int h = idx / KC, kk2 = idx % KC;
         const int code = tb.halo_src[hoff + h];
         const int kq = kc * KC + kk2;
         htab[idx] = code >= 0 ? (long long)(qplane(code >> 4, 0, kq, Q) * 16 + (code & 15)) : -((long long)(-code - 2) * Q * NLEV + kq) - 1;
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
           cl = make_double2(P_sp[r].x * (dps0 - a.dt * P_dd[r].x), P_sp[r].y * (dps1 - a.dt * P_dd[r].y));
           rcl = make_double2(1.0 / cl.x, 1.0 / cl.y);
         }
-        const int off = (c * GPL + ppl) * 16;
+        const int off = c * PCS + ppl * 16;
         if (cfg.U1 >= 0) *reinterpret_cast<double2*>(pp + cfg.U1 * PP_BYTES + off) = u1;
         if (cfg.U2 >= 0) *reinterpret_cast<double2*>(pp + cfg.U2 * PP_BYTES + off) = u2;
         if (cfg.CL >= 0) *reinterpret_cast<double2*>(pp + cfg.CL * PP_BYTES + off) = cl;
@@ -397,8 +400,8 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     TSE_UNROLL
     for (int c = 0; c < 8; c += 2) {
-      const double2 x0 = lds128(pp + cfg.CL * PP_BYTES, (c * GPL + pl) * 16);
-      const double2 x1 = lds128(pp + cfg.CL * PP_BYTES, ((c + 1) * GPL + pl) * 16);
+      const double2 x0 = lds128(pp + cfg.CL * PP_BYTES, c * PCS + pl * 16);
+      const double2 x1 = lds128(pp + cfg.CL * PP_BYTES, (c + 1) * PCS + pl * 16);
       s0 += x0.x; s1 += x0.y; s2 += x1.x; s3 += x1.y;
     }
     sumc = (s0 + s1) + (s2 + s3);
@@ -465,7 +468,7 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
       if (OP == OP_MINMAX || OP == OP_BIHARM_PRE) {
         TSE_UNROLL
         for (int c = 0; c < 8; ++c) {
-          const double2 rd = lds128(pp + cfg.RDP * PP_BYTES, (c * GPL + pl) * 16);
+          const double2 rd = lds128(pp + cfg.RDP * PP_BYTES, c * PCS + pl * 16);
           S[2 * c] *= rd.x;
           S[2 * c + 1] *= rd.y;
         }
@@ -538,7 +541,7 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
           double qv[16];
           TSE_UNROLL
           for (int c = 0; c < 8; ++c) {
-            const double2 rd = lds128(pp + cfg.RDP * PP_BYTES, (c * GPL + pl) * 16);
+            const double2 rd = lds128(pp + cfg.RDP * PP_BYTES, c * PCS + pl * 16);
             qv[2 * c] = S[2 * c] * rd.x;
             qv[2 * c + 1] = S[2 * c + 1] * rd.y;
           }

@@ -73,7 +73,13 @@ struct TileArgs {
   const int* glist;  // optional list of groups this launch covers (boundary groups first, interior groups while the halo is in flight)
 };
 
-constexpr int PP_BYTES = GPL * 128;  // per-plane package field (8 KB)
+// per-plane package field: 8 chunks (16 bytes = 2 nodes each) x GPL planes, chunk-major.  The chunk stride is padded by one
+// 16-byte unit: with a stride of exactly GPL*16 = 1 KB the 8 chunks of a plane fall into the same banks and the prologue's stores
+// (8 consecutive threads = the 8 chunks of one plane, so that the global loads are whole 128-byte lines) went 8-way conflicted
+// (7.6 % of all shared-memory wavefronts of a stage kernel); the consumers' reads (consecutive planes of one chunk) are
+// conflict-free either way.
+constexpr int PCS = GPL * 16 + 16;   // bytes between consecutive chunks of a package field
+constexpr int PP_BYTES = 8 * PCS;
 constexpr int EL_BYTES = GE * 128;   // per-element package field (2 KB)
 
 // which package fields an op keeps in shared memory
@@ -142,7 +148,7 @@ __device__ __forceinline__ unsigned any_outside(const double (&x)[16], double lo
 
 // limiter_optim_iter_full (prim_advection_mod.F90:976-1094).  On entry y = c*x (mass contributions, c = sphweights*dpmass);
 // c and rc = 1/c are read from the per-plane package in shared memory (cbase/rcbase = shared address of chunk 0 of this
-// plane, chunk stride GPL*16 bytes).  Sums use 4 interleaved partial accumulators (fixed order, identical on every GPU count).
+// plane, chunk stride PCS bytes).  Sums use 4 interleaved partial accumulators (fixed order, identical on every GPU count).
 //
 // Fast path: mass = sum(y) and the min/max relaxation (:1016-1029) need no x; if no x = y*rc lies outside [minp, maxp] the
 // reference's first sweep finds addmass = 0 and leaves (:1047), so y is returned untouched.
@@ -172,7 +178,7 @@ __device__ __forceinline__ unsigned limiter_check(const double (&y)[16], unsigne
   double x[16];
   TSE_UNROLL
   for (int cc = 0; cc < 8; ++cc) {
-    const double2 r = lds128v(rcbase + cc * GPL * 16);
+    const double2 r = lds128v(rcbase + cc * PCS);
     x[2 * cc] = y[2 * cc] * r.x;
     x[2 * cc + 1] = y[2 * cc + 1] * r.y;
   }
@@ -187,7 +193,7 @@ __device__ __forceinline__ void limiter_slow(double (&y)[16], unsigned cbase, un
   const double thresh = tol_limiter * fabs(mass);
   TSE_UNROLL
   for (int cc = 0; cc < 8; ++cc) {
-    const double2 r = lds128v(rcbase + cc * GPL * 16);
+    const double2 r = lds128v(rcbase + cc * PCS);
     y[2 * cc] *= r.x;
     y[2 * cc + 1] *= r.y;
   }
@@ -197,7 +203,7 @@ __device__ __forceinline__ void limiter_slow(double (&y)[16], unsigned cbase, un
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     TSE_UNROLL
     for (int cc = 0; cc < 8; cc += 2) {
-      const double2 ca = lds128v(cbase + cc * GPL * 16), cb = lds128v(cbase + (cc + 1) * GPL * 16);
+      const double2 ca = lds128v(cbase + cc * PCS), cb = lds128v(cbase + (cc + 1) * PCS);
       const int n = 2 * cc;
       ce[n] = ca.x; ce[n + 1] = ca.y; ce[n + 2] = cb.x; ce[n + 3] = cb.y;
       double t;
@@ -278,7 +284,7 @@ __device__ __forceinline__ void limiter_slow(double (&y)[16], unsigned cbase, un
   }
   TSE_UNROLL
   for (int cc = 0; cc < 8; ++cc) {
-    const double2 c = lds128v(cbase + cc * GPL * 16);
+    const double2 c = lds128v(cbase + cc * PCS);
     y[2 * cc] *= c.x;
     y[2 * cc + 1] *= c.y;
   }
@@ -312,14 +318,14 @@ __global__ void __launch_bounds__(GPL) k_debug_limiter(int n, double* __restrict
     } else {
       yy[2 * c] = yy[2 * c + 1] = 0.0;
     }
-    *reinterpret_cast<double2*>(pk + (c * GPL + pl) * 16) = cl;
-    *reinterpret_cast<double2*>(pk + PP_BYTES + (c * GPL + pl) * 16) = make_double2(1.0 / cl.x, 1.0 / cl.y);
+    *reinterpret_cast<double2*>(pk + c * PCS + pl * 16) = cl;
+    *reinterpret_cast<double2*>(pk + PP_BYTES + c * PCS + pl * 16) = make_double2(1.0 / cl.x, 1.0 / cl.y);
   }
   __syncthreads();
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
   TSE_UNROLL
   for (int c = 0; c < 8; c += 2) {
-    const double2 x0 = lds128(pk, (c * GPL + pl) * 16), x1 = lds128(pk, ((c + 1) * GPL + pl) * 16);
+    const double2 x0 = lds128(pk, c * PCS + pl * 16), x1 = lds128(pk, (c + 1) * PCS + pl * 16);
     s0 += x0.x; s1 += x0.y; s2 += x1.x; s3 += x1.y;
   }
   const double sumc = (s0 + s1) + (s2 + s3);
@@ -340,7 +346,7 @@ __device__ __forceinline__ void flux_div(const double (&S)[16], const unsigned c
                                          double (&y)[16]) {
   TSE_UNROLL
   for (int b = 0; b < 4; ++b) {
-    const double2 ua = lds128(u1, ((2 * b) * GPL + pl) * 16), ub = lds128(u1, ((2 * b + 1) * GPL + pl) * 16);
+    const double2 ua = lds128(u1, (2 * b) * PCS + pl * 16), ub = lds128(u1, (2 * b + 1) * PCS + pl * 16);
     const double g0 = ua.x * S[4 * b], g1 = ua.y * S[4 * b + 1], g2 = ub.x * S[4 * b + 2], g3 = ub.y * S[4 * b + 3];
     y[4 * b + 0] = fma(D.d[3 + 0], g3, fma(D.d[2 + 0], g2, fma(D.d[1 + 0], g1, D.d[0 + 0] * g0)));
     y[4 * b + 1] = fma(D.d[3 + 4], g3, fma(D.d[2 + 4], g2, D.d[0 + 4] * g0));   // Dvv(1,1) = 0
@@ -352,7 +358,7 @@ __device__ __forceinline__ void flux_div(const double (&S)[16], const unsigned c
     double ge[4], go[4];
     TSE_UNROLL
     for (int i = 0; i < 4; ++i) {
-      const double2 u = lds128(u2, ((h + 2 * i) * GPL + pl) * 16);
+      const double2 u = lds128(u2, (h + 2 * i) * PCS + pl * 16);
       ge[i] = u.x * S[2 * h + 4 * i];
       go[i] = u.y * S[2 * h + 1 + 4 * i];
     }
