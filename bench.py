@@ -324,7 +324,8 @@ def run_ours(args):
            "tracer_mass_hex": [float(x).hex() for x in mass[:6]], "tracer_qmin_qmax_hex": [[float(a).hex(), float(b).hex()] for a, b in zip(qmn[:6], qmx[:6])], "mass_drift_rel": mass_drift, "mass_drift_rel_checkerboard": mass_drift_fill, "device_bytes": int(adv.device_bytes),
            "published_context": "reference Fortran/MPI on 960 Edison cores: 42.6 s per model-hour = 39.4 tracer-steps/s (README:174)"}
     if not args.no_cpu and world == 1:
-        rate, cores, sample, _ = cpu_oracle_rate(ne, qsize, test, 1, 0)
+        # same sample and protocol as --impl reference, shortened: one warm-up cycle (first-touch of the oracle's arrays), one timed
+        rate, cores, sample, _ = cpu_oracle_rate(ne, qsize, test, 1, 1)
         out["cpu_baseline"] = {"value": rate, "unit": "tracer-steps/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(out))
     adv.close()
