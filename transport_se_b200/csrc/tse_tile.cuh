@@ -364,7 +364,8 @@ __device__ __forceinline__ void flux_div(const double (&S)[16], const unsigned c
     }
     TSE_UNROLL
     for (int b = 0; b < 4; ++b) {
-      double se = 0.0, so = 0.0;
+      // the second contraction continues the FMA chain of the first (no separate partial sum and add)
+      double se = y[2 * h + 4 * b], so = y[2 * h + 1 + 4 * b];
       TSE_UNROLL
       for (int i = 0; i < 4; ++i) {
         if (!(i == b && (b == 1 || b == 2))) {
@@ -372,8 +373,8 @@ __device__ __forceinline__ void flux_div(const double (&S)[16], const unsigned c
           so = fma(D.d[i + 4 * b], go[i], so);
         }
       }
-      y[2 * h + 4 * b] += se;
-      y[2 * h + 1 + 4 * b] += so;
+      y[2 * h + 4 * b] = se;
+      y[2 * h + 1 + 4 * b] = so;
     }
   }
 }
