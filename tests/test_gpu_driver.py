@@ -192,6 +192,13 @@ def test_full_dcmip_run_matches_readme_norms(built, ne, test, cycles, gold):
     qdp = np.zeros((m.nelem, 2, qsize, 72, 16))
     adv.copy_qdp_d2h(qdp, 1)
     q_i = qdp[:, 0, tracer] / dp_ic[None, :, None]
+    if test == 12:
+        # the checkerboard fillers (tracers 1, 3, 4 of DCMIP 1-2) are 1 where sin(9 lon) sin(9 lat) >= 0 and 0 elsewhere
+        # (dcmip_wrapper_mod.F90:215-243): the device's sin must take the same side as the host's libm on every node, also at ne120
+        # where nodes come within 1e-16 of the pattern's zero lines
+        board = (np.sin(9.0 * m.lon) * np.sin(9.0 * m.lat) >= 0.0).astype(np.float64)
+        for t in (0, 2, 3):
+            assert np.array_equal(qdp[:, 0, t] / dp_ic[None, :, None] > 0.5, np.broadcast_to(board[:, None, :] > 0.5, qdp[:, 0, t].shape))
     if ne <= 30:   # cross-check the host-side reconstruction of the initial state against the oracle's
         _, _, _, o = make_oracle(ne, qsize, test)
         assert relerr(q_i, o.Q[:, tracer]) < 1e-13 and relerr(z_mid, o.phi[0, :, 0] / 9.80616) < 1e-14
