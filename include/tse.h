@@ -133,6 +133,11 @@ int tse_euler_step(tse_handle h, int np1_qdp, int n0_qdp, double dt, int DSSopt,
 int tse_qdp_time_avg(tse_handle h, int rkstage, int n0_qdp, int np1_qdp);
 int tse_vertical_remap(tse_handle h, double dt, int np1, int np1_qdp);
 int tse_advec_tracers_remap_rk2(tse_handle h, double dt, int nstep);
+/* advance_hypervis_scalar_cuda(edgeAdv,elem,hvcoord,hybrid,deriv,nt,nt_qdp,nets,nete,dt2) (cuda_mod.F90:624-718): hypervis_subcycle_q
+ * subcycles of Qdp(nt_qdp) += -dt*nu_q*biharmonic(dp0*Qdp/dp) with dp = derived%dp - dt2*derived%divdp_proj, each followed by
+ * limiter2d_zero (:863-913) and the DSS.  No executable of the reference calls this routine (its CPU path applies the tracer
+ * hyperviscosity inside the third euler_step stage); it is a separate entry, never called by the other entries.  nu_p = 0 only. */
+int tse_advance_hypervis_scalar(tse_handle h, int nt_qdp, double dt2);
 
 /* Device-side test-case driver (prim_advance_exp + prim_step + prim_run_subcycle sequencing,
  * prim_advance_mod.F90:70-152, prim_driver_mod.F90:701-943) for test_case 11 (DCMIP 1-1) / 12 (DCMIP 1-2). */

@@ -610,6 +610,84 @@ void biharmonic_wk_scalar_minmax(Oracle& o, std::vector<double>& qtens) {
 }
 
 // ---------------------------------------------------------------------------
+// advance_hypervis_scalar_cuda, src/share/cuda_mod.F90:624-718 with its kernels hypervis_kernel1 / hypervis_kernel2
+// (:1292-1360), limiter2d_zero_kernel (:863-913) and euler_hypervis_kernel_last (:917-928).  NOTE: no executable of the reference
+// calls this routine (the CPU build has no advance_hypervis_scalar at all; the CUDA module only declares it
+// public); it is restated here because the coverage contract lists it.  nu_p = 0 branch only (dpdiss_ave is not
+// part of the mini-app's state); variable_hyperviscosity = 1 (hypervis_power = 0).
+//     dt = dt2 / hypervis_subcycle_q;  per subcycle:
+//       dp    = derived%dp - dt2*derived%divdp_proj                                   (:643-646, dt2, not dt)
+//       qtens = laplace_sphere_wk( dp0(k) * Qdp/dp )                                  kernel 1
+//       DSS(qtens)                                                                    (plain sum over the sharing elements)
+//       Qdp   = Qdp*spheremp - dt*nu_q*laplace_sphere_wk( rspheremp*qtens )           kernel 2
+//       limiter2d_zero(Qdp)  (every level: make the element mass-weighted values non-negative, mass preserving)
+//       DSS(Qdp);  Qdp = rspheremp*Qdp                                               kernel 3
+// ---------------------------------------------------------------------------
+void limiter2d_zero_plane(double* q) {  // cuda_mod.F90:863-913, one (level, tracer) plane, values already spheremp-weighted
+  double mass = 0.0;
+  for (int jj = 0; jj < 16; ++jj) mass = mass + q[jj];
+  if (mass < 0) for (int n = 0; n < 16; ++n) q[n] = -q[n];
+  for (int n = 0; n < 16; ++n) if (q[n] < 0) q[n] = 0;
+  double mass_new = 0.0;
+  for (int jj = 0; jj < 16; ++jj) mass_new = mass_new + q[jj];
+  if (mass_new > 0) for (int n = 0; n < 16; ++n) q[n] = q[n] * std::fabs(mass) / mass_new;
+  if (mass < 0) for (int n = 0; n < 16; ++n) q[n] = -q[n];
+}
+void advance_hypervis_scalar(Oracle& o, int nt_qdp, double dt2, int hypervis_subcycle_q) {
+  if (o.nu_q == 0) return;
+  const int nlev = o.nlev, qsize = o.qsize, nl = nlev * qsize;
+  const double dt = dt2 / hypervis_subcycle_q;
+  std::vector<double> qtens((size_t)o.nelem * nl * 16);
+  ensure_buf(o, nl);
+  for (int ic = 0; ic < hypervis_subcycle_q; ++ic) {
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < o.nelem; ++e) {
+      ElemGeo ge = o.geo(e);
+      for (int q = 0; q < qsize; ++q)
+        for (int k = 0; k < nlev; ++k) {
+          const double dp0 = (o.hyai[k + 1] - o.hyai[k]) * o.ps0 + (o.hybi[k + 1] - o.hybi[k]) * o.ps0;
+          const double* q0 = o.qdp(e, nt_qdp, q, k);
+          double sarr[16];
+          for (int n = 0; n < 16; ++n) {
+            const double dp = o.lev(o.dp, e, k)[n] - dt2 * o.lev(o.divdp_proj, e, k)[n];
+            sarr[n] = dp0 * q0[n] / dp;
+          }
+          laplace_sphere_wk(sarr, o.dvv.data(), ge, &qtens[(((size_t)e * qsize + q) * nlev + k) * 16]);
+        }
+      edgeVpack(o, &qtens[(size_t)e * nl * 16], nl, 0, e);
+    }
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < o.nelem; ++e) {
+      ElemGeo ge = o.geo(e);
+      double* qt = &qtens[(size_t)e * nl * 16];
+      edgeVunpack(o, qt, nl, 0, e);
+      for (int q = 0; q < qsize; ++q)
+        for (int k = 0; k < nlev; ++k) {
+          double sarr[16], lap[16];
+          double* t = qt + ((size_t)q * nlev + k) * 16;
+          for (int n = 0; n < 16; ++n) sarr[n] = ge.rspheremp[n] * t[n];
+          laplace_sphere_wk(sarr, o.dvv.data(), ge, lap);
+          double* q1 = o.qdp(e, nt_qdp, q, k);
+          for (int n = 0; n < 16; ++n) q1[n] = q1[n] * ge.spheremp[n] - dt * o.nu_q * lap[n];
+          limiter2d_zero_plane(q1);
+        }
+    }
+    // second exchange: all elements must have finished the first unpack before the buffer is reused
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < o.nelem; ++e) edgeVpack(o, o.qdp(e, nt_qdp, 0, 0), nl, 0, e);
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < o.nelem; ++e) {
+      ElemGeo ge = o.geo(e);
+      edgeVunpack(o, o.qdp(e, nt_qdp, 0, 0), nl, 0, e);
+      for (int l = 0; l < nl; ++l) {
+        double* q1 = o.qdp(e, nt_qdp, 0, 0) + (size_t)l * 16;
+        for (int n = 0; n < 16; ++n) q1[n] = ge.rspheremp[n] * q1[n];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // euler_step, prim_advection_mod.F90:667-970
 // ---------------------------------------------------------------------------
 double* dss_var(Oracle& o, int DSSopt, int e) {
@@ -1109,6 +1187,9 @@ void orc_qdp_time_avg(void* h, int rkstage, int n0_qdp, int np1_qdp) { qdp_time_
 void orc_advec_tracers_remap_rk2(void* h, double dt) { advec_tracers_remap_rk2(*(Oracle*)h, dt); }
 int orc_vertical_remap(void* h, double dt, int np1, int np1_qdp) { return vertical_remap(*(Oracle*)h, dt, np1, np1_qdp); }
 void orc_neighbor_minmax(void* h) { neighbor_minmax(*(Oracle*)h); }
+void orc_advance_hypervis_scalar(void* h, int nt_qdp, double dt2, int hypervis_subcycle_q) {
+  advance_hypervis_scalar(*(Oracle*)h, nt_qdp, dt2, hypervis_subcycle_q);
+}
 // DSS of nlyr planes per element held in `field` ([e][nlyr][16]); used by tests
 void orc_dss(void* h, double* field, int nlyr) {
   Oracle& o = *(Oracle*)h;

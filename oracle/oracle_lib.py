@@ -50,6 +50,7 @@ def lib():
         L.orc_vertical_remap.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
         L.orc_vertical_remap.restype = C.c_int
         L.orc_neighbor_minmax.argtypes = [C.c_void_p]
+        L.orc_advance_hypervis_scalar.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
         L.orc_dss.argtypes = [C.c_void_p, _dp, C.c_int]
         L.orc_global_integral.restype = C.c_double
         L.orc_global_integral.argtypes = [C.c_void_p, _dp, _dp]
@@ -155,6 +156,10 @@ class Oracle:
 
     def neighbor_minmax(self):
         lib().orc_neighbor_minmax(self._h)
+
+    def advance_hypervis_scalar(self, nt_qdp, dt2, hypervis_subcycle_q=1):
+        """cuda_mod.F90:624-718 (not on the reference's CPU path; see the note in oracle.cpp)"""
+        lib().orc_advance_hypervis_scalar(self._h, nt_qdp, dt2, hypervis_subcycle_q)
 
     def dss(self, field):
         assert field.flags.c_contiguous and field.shape[0] == self.nelem and field.shape[-1] == 16

@@ -48,7 +48,7 @@ EXPORTS = ["tse_last_error", "tse_device_count", "tse_init", "tse_finalize", "ts
            "tse_precompute_divdp", "tse_euler_step", "tse_qdp_time_avg", "tse_vertical_remap", "tse_advec_tracers_remap_rk2",
            "tse_dcmip_init", "tse_prim_run_subcycle", "tse_diag_mass", "tse_diag_qminmax", "tse_timer_ms", "tse_launch_count",
            "tse_device_bytes", "tse_timer_reset", "tse_mark", "tse_mark_elapsed_ms", "tse_get_wind", "tse_stage_launch_count", "tse_halo_bytes",
-           "tse_debug_limiter", "tse_diag_field_hash"]
+           "tse_debug_limiter", "tse_diag_field_hash", "tse_advance_hypervis_scalar"]
 
 
 def _preload_bundled_nccl():
@@ -96,6 +96,7 @@ def cuda_lib():
         L.tse_qdp_time_avg.argtypes = [vp, i, i, i]
         L.tse_vertical_remap.argtypes = [vp, d, i, i]
         L.tse_advec_tracers_remap_rk2.argtypes = [vp, d, i]
+        L.tse_advance_hypervis_scalar.argtypes = [vp, i, d]
         L.tse_dcmip_init.argtypes = [vp, i]
         L.tse_prim_run_subcycle.argtypes = [vp, d, _ip]
         L.tse_diag_mass.argtypes = [vp, i, _dp]
@@ -225,6 +226,10 @@ class TracerAdvection:
 
     def vertical_remap(self, dt, np1, np1_qdp):
         self._ck(self._L.tse_vertical_remap(self._h, dt, np1, np1_qdp))
+
+    def advance_hypervis_scalar(self, nt_qdp, dt2):
+        """advance_hypervis_scalar_cuda (cuda_mod.F90:624-718): subcycled tracer hyperviscosity + limiter2d_zero; separate entry."""
+        self._ck(self._L.tse_advance_hypervis_scalar(self._h, nt_qdp, dt2))
 
     def prim_advec_tracers_remap_rk2(self, dt, nstep):
         self._ck(self._L.tse_advec_tracers_remap_rk2(self._h, dt, nstep))

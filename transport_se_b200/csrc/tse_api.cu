@@ -802,6 +802,7 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
   TSE_TILE_SMEM(OP_TIME_AVG);
   TSE_TILE_SMEM(OP_RESOLVE);
   TSE_TILE_SMEM(OP_MASS);
+  TSE_TILE_SMEM(OP_HYPERVIS);
 #undef TSE_TILE_SMEM
   CU(cudaStreamSynchronize(s->stream));
   guard.p = nullptr;
@@ -1027,27 +1028,29 @@ int tse_precompute_divdp(tse_handle s) {
   return 0;
 }
 
-int tse_euler_step(tse_handle s, int np1_qdp, int n0_qdp, double dt, int DSSopt, int rhs_multiplier) {
-  if (!s) return fail("tse_euler_step: null handle");
-  if (poll_device_error(s)) return 1;
-  if (check_tl(np1_qdp) || check_tl(n0_qdp)) return 1;
-  if (rhs_multiplier < 0 || rhs_multiplier > 2) return fail("tse_euler_step: rhs_multiplier=%d", rhs_multiplier);
-  ScopedTimer tm(s, "euler_step");
+// One stage of the euler_step family.  tse_euler_step and tse_advance_hypervis_scalar differ only in these numbers.
+struct StageParams {
+  double dt_adv;       // dt of the advective part (0: none)
+  double rhs_mult_dt;  // dp = derived%dp - rhs_mult_dt * derived%divdp_proj
+  double visc_coef;    // Qtens += visc_coef * dp0(k) * biharmonic / spheremp        (stage kind 2 only)
+  int limiter8;        // limiter_optim_iter_full on the result
+  int limiter_zero;    // limiter2d_zero on the result
+  int need_bounds;     // compute qmin/qmax (neighbor_minmax)
+  int store_bounds;    // write the relaxed bounds back
+};
+static int euler_stage(tse_state* s, int np1_qdp, int n0_qdp, int DSSopt, int rhs_multiplier, const StageParams& sp) {
   const int in = s->slot_buf[n0_qdp], in_pending = s->slot_pending[n0_qdp];
   const int other = (np1_qdp == n0_qdp) ? s->slot_buf[3 - np1_qdp] : -1;  // the untouched time level
   TileArgs a = tile_args(s);
-  a.rhs_mult_dt = rhs_multiplier * dt;
-  a.dt = dt;
-  a.visc_coef = -3.0 * dt * s->cfg.nu_q;  // rhs_viss = 3 (prim_advection_mod.F90:797,823)
-  // Stage 2 reads the bounds stage 1 relaxed; stage 3 starts from fresh extrema (:797-806), so what stages 2 and 3 would write
-  // back is never read on the path.  The fused driver skips those stores; the stage-by-stage entry keeps them for tse_get_qminmax.
-  a.store_bounds = (rhs_multiplier == 0 || !s->fused_step) ? 1 : 0;
+  a.rhs_mult_dt = sp.rhs_mult_dt;
+  a.dt = sp.dt_adv;
+  a.visc_coef = sp.visc_coef;
+  a.limiter8 = sp.limiter8;
+  a.store_bounds = sp.store_bounds;
   int tmp = -1;
   if (wait_halo(s)) return 1;
-  if (rhs_multiplier == 0 && (a.limiter8 || !s->fused_step)) {
-    // qmin/qmax = element extrema of Q = Qdp/dp, then min/max over the 8 neighbours (:764-778).  Without limiter 8 nothing reads
-    // them (the reference computes them all the same): the fused driver skips the pass, the stage-by-stage entry keeps it so
-    // that tse_get_qminmax returns what the reference holds.
+  if (rhs_multiplier == 0 && sp.need_bounds) {
+    // qmin/qmax = element extrema of Q = Qdp/dp, then min/max over the 8 neighbours (:764-778)
     set_src(s, a, 0, in, in_pending);
     if (launch_tile_overlapped<OP_MINMAX>(s, a, [&]() { return pack_minmax(s) || exchange(s, {xfer_minmax(s)}); })) return 1;
     if (neighbor_minmax(s)) return 1;
@@ -1061,7 +1064,7 @@ int tse_euler_step(tse_handle s, int np1_qdp, int n0_qdp, double dt, int DSSopt,
     if (launch_tile_overlapped<OP_BIHARM_PRE>(
             s, a, [&]() { return pack_tracer(s, tmp) || pack_minmax(s) || exchange(s, {xfer_tracer(s, tmp), xfer_minmax(s)}); }))
       return 1;
-    if (neighbor_minmax(s)) return 1;
+    if (sp.need_bounds && neighbor_minmax(s)) return 1;
   }
   const int outb = pick_buffer({in, other, tmp});
   if (outb < 0) return fail("tse_euler_step: no free tracer buffer");
@@ -1080,7 +1083,9 @@ int tse_euler_step(tse_handle s, int np1_qdp, int n0_qdp, double dt, int DSSopt,
     if (rhs_multiplier == 2) {
       set_src(s, a, 0, tmp, 1);
       set_src(s, a, 1, in, in_pending);
-      if (launch_tile_overlapped<OP_STAGE3>(s, a, stage_comm)) return 1;
+      if (sp.limiter_zero) {
+        if (launch_tile_overlapped<OP_HYPERVIS>(s, a, stage_comm)) return 1;
+      } else if (launch_tile_overlapped<OP_STAGE3>(s, a, stage_comm)) return 1;
     } else {
       set_src(s, a, 0, in, in_pending);
       if (rhs_multiplier == 0) {
@@ -1092,6 +1097,55 @@ int tse_euler_step(tse_handle s, int np1_qdp, int n0_qdp, double dt, int DSSopt,
   s->slot_buf[np1_qdp] = outb;
   s->slot_pending[np1_qdp] = 1;
   return dss_level_field(s, DSSopt);
+}
+
+int tse_euler_step(tse_handle s, int np1_qdp, int n0_qdp, double dt, int DSSopt, int rhs_multiplier) {
+  if (!s) return fail("tse_euler_step: null handle");
+  if (poll_device_error(s)) return 1;
+  if (check_tl(np1_qdp) || check_tl(n0_qdp)) return 1;
+  if (rhs_multiplier < 0 || rhs_multiplier > 2) return fail("tse_euler_step: rhs_multiplier=%d", rhs_multiplier);
+  ScopedTimer tm(s, "euler_step");
+  StageParams sp{};
+  sp.dt_adv = dt;
+  sp.rhs_mult_dt = rhs_multiplier * dt;
+  sp.visc_coef = -3.0 * dt * s->cfg.nu_q;  // rhs_viss = 3 (prim_advection_mod.F90:797,823)
+  sp.limiter8 = s->cfg.limiter_option == 8 ? 1 : 0;
+  sp.limiter_zero = 0;
+  // Without limiter 8 nothing reads qmin/qmax (the reference computes them all the same): the fused driver skips the passes, the
+  // stage-by-stage entry keeps them so that tse_get_qminmax returns what the reference holds.
+  sp.need_bounds = (sp.limiter8 || !s->fused_step) ? 1 : 0;
+  // Stage 2 reads the bounds stage 1 relaxed; stage 3 starts from fresh extrema (:797-806), so what stages 2 and 3 would write
+  // back is never read on the path.  The fused driver skips those stores; the stage-by-stage entry keeps them for tse_get_qminmax.
+  sp.store_bounds = (rhs_multiplier == 0 || !s->fused_step) ? 1 : 0;
+  return euler_stage(s, np1_qdp, n0_qdp, DSSopt, rhs_multiplier, sp);
+}
+
+// advance_hypervis_scalar_cuda (cuda_mod.F90:624-718; kernels :1292-1360, :863-913, :917-928).  No executable of the reference
+// calls it; it is provided as a separate entry for hosts that want HOMME's forward-in-time tracer hyperviscosity with the
+// zero limiter.  Per subcycle (dt = dt2/hypervis_subcycle_q):
+//   qtens = lap( dp0*Qdp/(derived%dp - dt2*divdp_proj) );  DSS;  Qdp = spheremp*Qdp - dt*nu_q*lap(rspheremp*qtens);
+//   limiter2d_zero;  DSS;  Qdp *= rspheremp
+// which is the stage-3 machinery (OP_BIHARM_PRE + OP_STAGE3) with the advective part switched off (dt_adv = 0), the viscous
+// coefficient -dt*nu_q (dp0 applied after the second laplacian: it is constant on a level) and the zero limiter on the result;
+// the last DSS is applied by the next reader, like after every stage.  nu_p = 0 branch only.
+int tse_advance_hypervis_scalar(tse_handle s, int nt_qdp, double dt2) {
+  if (!s) return fail("tse_advance_hypervis_scalar: null handle");
+  if (poll_device_error(s)) return 1;
+  if (check_tl(nt_qdp)) return 1;
+  if (s->cfg.nu_q == 0.0 || s->cfg.hypervis_order != 2) return 0;  // cuda_mod.F90:656-657
+  ScopedTimer tm(s, "advance_hypervis_scalar");
+  const int nsub = s->cfg.hypervis_subcycle_q > 0 ? s->cfg.hypervis_subcycle_q : 1;
+  StageParams sp{};
+  sp.dt_adv = 0.0;
+  sp.rhs_mult_dt = dt2;
+  sp.visc_coef = -(dt2 / nsub) * s->cfg.nu_q;
+  sp.limiter8 = 0;
+  sp.limiter_zero = 1;
+  sp.need_bounds = 0;
+  sp.store_bounds = 0;
+  for (int ic = 0; ic < nsub; ++ic)
+    if (euler_stage(s, nt_qdp, nt_qdp, TSE_DSS_NO_VAR, 2, sp)) return 1;
+  return 0;
 }
 
 int tse_qdp_time_avg(tse_handle s, int rkstage, int n0_qdp, int np1_qdp) {

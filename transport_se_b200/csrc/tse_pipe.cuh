@@ -151,8 +151,9 @@ __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %
 template <int OP>
 __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 : pipe_minb(OP))) k_pipe(const __grid_constant__ PipeMaps maps, Geo G, Dvv D, TileTables tb, TileArgs a) {
   constexpr TileCfg cfg = tile_cfg(OP);
-  constexpr bool kStage = (OP == OP_STAGE1 || OP == OP_STAGE2 || OP == OP_STAGE3);
-  constexpr int NIN = (OP == OP_STAGE3 || OP == OP_TIME_AVG) ? 2 : 1;
+  constexpr bool kS3 = (OP == OP_STAGE3 || OP == OP_HYPERVIS);
+  constexpr bool kStage = (OP == OP_STAGE1 || OP == OP_STAGE2 || kS3);
+  constexpr int NIN = (kS3 || OP == OP_TIME_AVG) ? 2 : 1;
   constexpr bool kHasOut = cfg.has_out != 0;
   constexpr int NST = pipe_nst(OP), NOUT = pipe_nout(OP), NPW = pipe_npw(OP);
   extern __shared__ unsigned char smem_raw[];
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
   // All global loads of the prologue are issued before the first of them is used (no branches in between: padded elements
   // read the last real element, their planes are never computed): one memory round trip instead of six dependent ones.
   // With 2 CTAs per SM the consumer warps of a starting CTA otherwise sit out ~25 % of the CTA's lifetime here.
-  const bool main_pending = (OP == OP_STAGE3) ? (a.pending[1] != 0) : (a.pending[0] != 0);
+  const bool main_pending = kS3 ? (a.pending[1] != 0) : (a.pending[0] != 0);
   const int elast = G.nelem - 1;
   double2 L_sp = make_double2(0, 0), L_rs = L_sp, L_rm = L_sp, L_t11 = L_sp, L_t12 = L_sp, L_t22 = L_sp;
   const bool el_thread = cfg.nel > 0 && t < GE * 8;
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
     }
     sumc = (s0 + s1) + (s2 + s3);
   }
-  const double cf = (OP == OP_STAGE3) ? a.visc_coef * a.dp0[k] : 0.0;
+  const double cf = kS3 ? a.visc_coef * a.dp0[k] : 0.0;
   const double rkm1 = a.rkstage - 1.0, rrk = 1.0 / a.rkstage;
 
   double keep[16];  // STAGE3: cf*lap of the first item; TIME_AVG: Qdp(n0)
@@ -521,7 +522,7 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
             S[2 * c + 1] = (keep[2 * c + 1] + rkm1 * (rs.y * S[2 * c + 1])) * rrk;
           }
         }
-      } else if (OP == OP_STAGE3 && which == 0) {
+      } else if (kS3 && which == 0) {
         // second half of biharmonic_wk_scalar_minmax: lap(rspheremp*DSS(qtens)); Qtens_biharmonic*spheremp = cf*lap
         TSE_UNROLL
         for (int c = 0; c < 8; ++c) {
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
           const double2 e2 = lds128v(e2a + c * GE * 16);
           y[2 * c] = fma(-e2.x, y[2 * c], e1.x * S[2 * c]);
           y[2 * c + 1] = fma(-e2.y, y[2 * c + 1], e1.y * S[2 * c + 1]);
-          if (OP == OP_STAGE3) {
+          if (kS3) {
             y[2 * c] += keep[2 * c];
             y[2 * c + 1] += keep[2 * c + 1];
           }
@@ -579,7 +580,8 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
 #ifndef TSE_SKIP_LIMITER
         const unsigned cl_a = smem_u32 + (unsigned)(pp - smem) + (cfg.CL < 0 ? 0 : cfg.CL) * PP_BYTES + pl * 16;
         const unsigned rc_a = smem_u32 + (unsigned)(pp - smem) + (cfg.RC < 0 ? 0 : cfg.RC) * PP_BYTES + pl * 16;
-        if (a.limiter8) limiter_y(y, cl_a, rc_a, sumc, minp, maxp);  // (:880: only option 8 limits inside euler_step)
+        if (OP == OP_HYPERVIS) limiter2d_zero(y);
+        else if (a.limiter8) limiter_y(y, cl_a, rc_a, sumc, minp, maxp);  // (:880: only option 8 limits inside euler_step)
 #endif
         asm volatile("" ::: "memory");
         if (a.store_bounds) {  // the relaxed bounds (:1024-1029) are only read again by stage 2 (and by tse_get_qminmax)

@@ -44,7 +44,9 @@ static_assert(EPW > 1 || (TT / 8) % GPL == 0 || GPL % (TT / 8) == 0, "swizzle");
 // (lanes 0..7 = 4 levels x 2 elements for EPW > 1, 4 levels x 2 tracers for EPW == 1)
 __host__ __device__ constexpr int swz(int p) { return EPW > 1 ? (p & 7) : ((p & 3) | (((p / GPL) & 1) << 2)); }
 
-enum TileOp { OP_MINMAX = 0, OP_STAGE1, OP_STAGE2, OP_STAGE3, OP_BIHARM_PRE, OP_TIME_AVG, OP_RESOLVE, OP_MASS };
+enum TileOp { OP_MINMAX = 0, OP_STAGE1, OP_STAGE2, OP_STAGE3, OP_BIHARM_PRE, OP_TIME_AVG, OP_RESOLVE, OP_MASS, OP_HYPERVIS };
+// OP_HYPERVIS = OP_STAGE3's data flow (second laplacian of the first input, added to the second) with the zero limiter instead of
+// limiter 8: its own instantiation so that the hot stage kernels do not carry the extra code (tse_advance_hypervis_scalar)
 
 struct TileTables {
   const int* gsrc_t;    // [npad][NSLOT]: <0 none, [0,256) in-group (el<<4|node), >=256 halo entry (code-256)
@@ -91,7 +93,7 @@ struct TileCfg {
 __host__ __device__ constexpr TileCfg tile_cfg(int op) {
   return op == OP_STAGE1 ? TileCfg{4, 2, 1, 0, 1, 2, -1, 3, 0, 1, -1, -1, -1, -1}
        : op == OP_STAGE2 ? TileCfg{5, 2, 1, 0, 1, 2, 3, 4, 0, 1, -1, -1, -1, -1}
-       : op == OP_STAGE3 ? TileCfg{4, 6, 1, 0, 1, 2, -1, 3, 0, 1, 2, 3, 4, 5}
+       : (op == OP_STAGE3 || op == OP_HYPERVIS) ? TileCfg{4, 6, 1, 0, 1, 2, -1, 3, 0, 1, 2, 3, 4, 5}
        : op == OP_MINMAX ? TileCfg{1, 0, 0, -1, -1, -1, 0, -1, -1, -1, -1, -1, -1, -1}
        : op == OP_BIHARM_PRE ? TileCfg{1, 3, 1, -1, -1, -1, 0, -1, -1, -1, -1, 0, 1, 2}
        : op == OP_MASS ? TileCfg{0, 2, 0, -1, -1, -1, -1, -1, 0, -1, 1, -1, -1, -1}   // E1 slot = spheremp (unscaled), RSPH
@@ -158,6 +160,32 @@ __device__ __forceinline__ unsigned any_outside(const double (&x)[16], double lo
 // bound -minp for the downward case (negation is exact) leaves one code path, whose sweep fuses "add the increment"
 // (:1052-1078 of sweep i), "clip" (:1037-1045 of sweep i+1) and the next weightssum; the weight of a node is carried in a
 // register and zeroed when the node reaches the bound, which removes the per-node "still below the bound?" tests.
+// limiter2d_zero (cuda_mod.F90:863-913 / prim_advection_mod.F90:1186-1234) on one plane of spheremp-weighted values: flip the sign
+// if the plane's mass is negative, zero the negative nodes, rescale the others to the original mass.  Sums in the reference's
+// node order.
+__device__ __forceinline__ void limiter2d_zero(double (&y)[16]) {
+  double mass = 0.0;
+  TSE_UNROLL
+  for (int n = 0; n < 16; ++n) mass = mass + y[n];
+  const bool negm = mass < 0.0;
+  double mass_new = 0.0;
+  TSE_UNROLL
+  for (int n = 0; n < 16; ++n) {
+    double v = negm ? -y[n] : y[n];
+    v = v < 0.0 ? 0.0 : v;
+    mass_new = mass_new + v;
+    y[n] = v;
+  }
+  if (mass_new > 0.0) {
+    TSE_UNROLL
+    for (int n = 0; n < 16; ++n) y[n] = y[n] * fabs(mass) / mass_new;
+  }
+  if (negm) {
+    TSE_UNROLL
+    for (int n = 0; n < 16; ++n) y[n] = -y[n];
+  }
+}
+
 // limiter_check: mass, relaxation of the bounds, and the test "does any node leave [minp, maxp]".  Returns 1 if the slow path has
 // to run (y is untouched either way).  Requires sumc > 0.
 __device__ __forceinline__ unsigned limiter_check(const double (&y)[16], unsigned rcbase, double sumc, double& minp, double& maxp, double& mass) {
