@@ -25,6 +25,7 @@ module tse_mod
 
   ! ---- the reference's hook names (cuda_mod.F90) --------------------------------------------------------------------
   public :: cuda_mod_init, copy_qdp_h2d, copy_qdp_d2h, euler_step_cuda, qdp_time_avg_cuda, vertical_remap_cuda
+  public :: advance_hypervis_scalar_cuda
   ! ---- extras of the new library ------------------------------------------------------------------------------------
   public :: tse_shim_finalize, tse_shim_set_derived, tse_shim_precompute_divdp, tse_shim_advec_tracers_remap_rk2
   public :: tse_shim_diag_mass, tse_shim_diag_qminmax, tse_shim_field_hash, tse_shim_synchronize
@@ -162,6 +163,13 @@ module tse_mod
       type(c_ptr),    value :: handle
       real(c_double), value :: dt
       integer(c_int), value :: nstep
+      integer(c_int) :: rc
+    end function
+    function tse_advance_hypervis_scalar(handle, nt_qdp, dt2) bind(C, name='tse_advance_hypervis_scalar') result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr),    value :: handle
+      integer(c_int), value :: nt_qdp
+      real(c_double), value :: dt2
       integer(c_int) :: rc
     end function
     function tse_dcmip_init(handle, test_case) bind(C, name='tse_dcmip_init') result(rc)
@@ -449,6 +457,24 @@ contains
     !$OMP END MASTER
     !$OMP BARRIER
   end subroutine vertical_remap_cuda
+
+  !> advance_hypervis_scalar_cuda (cuda_mod.F90:624-718): same argument list; derived%dp / divdp_proj must be on the device
+  !! (tse_shim_set_derived + the stages of the step have put them there)
+  subroutine advance_hypervis_scalar_cuda(edgeAdv, elem, hvcoord, hybrid, deriv, nt, nt_qdp, nets, nete, dt2)
+    use edge_mod, only : EdgeBuffer_t
+    type(EdgeBuffer_t),   intent(inout) :: edgeAdv
+    type(element_t),      intent(inout), target :: elem(:)
+    type(hvcoord_t),      intent(in) :: hvcoord
+    type(hybrid_t),       intent(in) :: hybrid
+    type(derivative_t),   intent(in) :: deriv
+    integer,              intent(in) :: nt, nt_qdp, nets, nete
+    real(kind=real_kind), intent(in) :: dt2
+    !$OMP BARRIER
+    !$OMP MASTER
+    call check(tse_advance_hypervis_scalar(h, int(nt_qdp, c_int), real(dt2, c_double)), 'advance_hypervis_scalar_cuda')
+    !$OMP END MASTER
+    !$OMP BARRIER
+  end subroutine advance_hypervis_scalar_cuda
 
   !> the whole of Prim_Advec_Tracers_remap_rk2 (prim_advection_mod.F90:579-640) in one call; nstep = tl%nstep
   subroutine tse_shim_advec_tracers_remap_rk2(elem, dt, nstep)
