@@ -1,6 +1,6 @@
 """Multi-GPU check, run under torchrun (one rank per GPU):
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py [ne] [qsize] [test] [cycles]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py [ne] [qsize] [test] [cycles] [limiter_option]
 
 Every rank advances its space-filling-curve chunk of the sphere (halo exchange over NCCL); rank 0 also advances the whole
 sphere alone on its GPU.  The N-rank result must be BIT-FOR-BIT the single-rank result (BASELINE.json north_star), and the
@@ -27,6 +27,7 @@ def main():
     qsize = int(sys.argv[2]) if len(sys.argv) > 2 else 5
     test = int(sys.argv[3]) if len(sys.argv) > 3 else 11
     cycles = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+    limiter_option = int(sys.argv[5]) if len(sys.argv) > 5 else 8
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -34,7 +35,7 @@ def main():
     tstep, nu_q = TSTEP.get(ne, 300.0), NU_Q.get(ne, 1e15)
 
     def run(view, with_comm):
-        adv = TracerAdvection(mesh, view, hv, qsize=qsize, nu_q=nu_q, device=local)
+        adv = TracerAdvection(mesh, view, hv, qsize=qsize, nu_q=nu_q, device=local, limiter_option=limiter_option)
         if with_comm:
             adv.comm_init(dist, rank, world)
         adv.dcmip_init(test)
@@ -57,6 +58,7 @@ def main():
         adv.euler_step(np1, tl, tstep / 2, DSSdiv_vdp_ave, 0)
         adv.euler_step(np1, np1, tstep / 2, DSSeta, 1)
         adv.euler_step(np1, np1, tstep / 2, DSSno_var, 2)
+        adv.advance_hypervis_scalar(np1, tstep)   # the separate hyperviscosity entry: two more exchanges through the same paths
         mass_p = adv.diag_mass(np1)
         qmn_p, qmx_p = adv.diag_qminmax(np1)
         fh_p = adv.diag_field_hash(np1)
@@ -84,9 +86,9 @@ def main():
                     ok = False
                     print("%s differs from the single-rank run:" % nm, x, y)
         same_q, same_p, same_qp = np.array_equal(qn, q1), np.array_equal(pn, proj1), np.array_equal(qpn, qp1)
-        print("mgpu_check ne=%d qsize=%d test=%d ranks=%d: Qdp bitwise %s, divdp_proj bitwise %s, Qdp after 3 more stages (resolved "
+        print("mgpu_check ne=%d qsize=%d test=%d limiter=%d ranks=%d: Qdp bitwise %s, divdp_proj bitwise %s, Qdp after 3 more stages (resolved "
               "from a pending level) bitwise %s, diagnostics bitwise %s, max|dQ|=%.3e, halo bytes/rank %s"
-              % (ne, qsize, test, world, same_q, same_p, same_qp, ok, np.max(np.abs(qn - q1)), [p[4] for p in parts]))
+              % (ne, qsize, test, limiter_option, world, same_q, same_p, same_qp, ok, np.max(np.abs(qn - q1)), [p[4] for p in parts]))
         ok = ok and same_q and same_p and same_qp
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

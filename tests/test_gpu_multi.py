@@ -14,13 +14,13 @@ def _ngpu():
     return cuda_lib().tse_device_count()
 
 
-@pytest.mark.parametrize("nranks,ne,test", [(2, 8, 11), (2, 8, 12), (4, 8, 11), (8, 30, 11)])
-def test_bit_for_bit_across_gpu_counts(nranks, ne, test):
+@pytest.mark.parametrize("nranks,ne,test,limiter", [(2, 8, 11, 8), (2, 8, 12, 8), (2, 8, 11, 0), (4, 8, 11, 8), (8, 30, 11, 8)])
+def test_bit_for_bit_across_gpu_counts(nranks, ne, test, limiter):
     n = _ngpu()
     if n < nranks:
         pytest.skip("needs %d GPUs, this box has %d" % (nranks, n))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks), "--master-addr", "127.0.0.1",
-           "--master-port", str(29500 + nranks + ne), os.path.join(ROOT, "tests", "mgpu_check.py"), str(ne), "5", str(test), "2"]
+           "--master-port", str(29500 + nranks + ne + limiter), os.path.join(ROOT, "tests", "mgpu_check.py"), str(ne), "5", str(test), "2", str(limiter)]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     print(r.stdout[-3000:])
     assert r.returncode == 0

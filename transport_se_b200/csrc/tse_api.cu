@@ -1064,7 +1064,8 @@ static int euler_stage(tse_state* s, int np1_qdp, int n0_qdp, int DSSopt, int rh
     if (launch_tile_overlapped<OP_BIHARM_PRE>(
             s, a, [&]() { return pack_tracer(s, tmp) || pack_minmax(s) || exchange(s, {xfer_tracer(s, tmp), xfer_minmax(s)}); }))
       return 1;
-    if (sp.need_bounds && neighbor_minmax(s)) return 1;
+    // the stage kernel gathers lap(Q) of off-GPU neighbours from the ghosts: the exchange must have landed either way
+    if (sp.need_bounds ? neighbor_minmax(s) : wait_halo(s)) return 1;
   }
   const int outb = pick_buffer({in, other, tmp});
   if (outb < 0) return fail("tse_euler_step: no free tracer buffer");
