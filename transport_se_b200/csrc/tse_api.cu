@@ -430,7 +430,7 @@ int dss_level_field(tse_state* s, int DSSopt) {  // the halo of the field (ghost
   if (DSSopt != TSE_DSS_NO_VAR && !f) return fail("tse_euler_step: DSSopt=%d", DSSopt);
   if (!f) return 0;
   if (wait_halo(s)) return 1;
-  k_dss_level<<<(unsigned)((s->ldoubles + 255) / 256), 256, 0, s->stream>>>(s->geo, *f, s->ghost_lev, s->lev_tmp);
+  k_dss_level<<<s->ngroups, DSL_THREADS, dss_level_smem_bytes(s->tiles.hmax), s->stream>>>(s->geo, s->tiles, *f, s->ghost_lev, s->lev_tmp);
   ++s->launches;
   CU(cudaGetLastError());
   std::swap(*f, s->lev_tmp);
@@ -803,6 +803,7 @@ int tse_init(const tse_config* cfg, const tse_geometry* geom, const tse_connecti
   TSE_TILE_SMEM(OP_RESOLVE);
   TSE_TILE_SMEM(OP_MASS);
   TSE_TILE_SMEM(OP_HYPERVIS);
+  CU(cudaFuncSetAttribute(k_dss_level, cudaFuncAttributeMaxDynamicSharedMemorySize, dss_level_smem_bytes(hm)));
 #undef TSE_TILE_SMEM
   CU(cudaStreamSynchronize(s->stream));
   guard.p = nullptr;

@@ -112,45 +112,6 @@ __global__ void __launch_bounds__(128) k_divdp(Geo G, Dvv D, const double* __res
   store16(divdp_proj + lp, r);
 }
 
-// DSS of one level field (the DSSopt variable of euler_step, prim_advection_mod.F90:913-919,943-958):
-// out = rspheremp * sum_{sharing elements} spheremp*f, in unpack order.  ghost: [slot][k] = spheremp*f of off-GPU nodes.
-// One thread per node (16 consecutive lanes = one plane: coalesced); a node receives at most 3 contributions, in the
-// order S, E, N, W edge then corner (slots of the gather table, -1 = none).
-__constant__ signed char c_node_slots[16][3] = {
-    {0, 12, 16}, {1, -1, -1}, {2, -1, -1},  {3, 4, 17},   // j = 0: S edge; node 0 also W and SW, node 3 also E and SE
-    {13, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {5, -1, -1},  // j = 1: W, interior, interior, E
-    {14, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {6, -1, -1},  // j = 2
-    {8, 15, 19}, {9, -1, -1}, {10, -1, -1}, {7, 11, 18}};  // j = 3: N edge; node 12 = N, W, NW; node 15 = E, N, NE
-__global__ void __launch_bounds__(256) k_dss_level(Geo G, const double* __restrict__ f, const double* __restrict__ ghost,
-                                                   double* __restrict__ out) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // node index in layout order
-  const size_t idx = i >> 4;                                        // level plane index in layout order
-  const int n = (int)(i & 15);
-  const int kk = idx % KC, el = (idx / KC) % GE;
-  const size_t gk = idx / GPL;
-  const int g = (int)(gk / NKC), kc = (int)(gk % NKC);
-  const int e = g * GE + el, k = kc * KC + kk;
-  if (g >= G.ngroups || e >= G.nelem) return;
-  // products are rounded before they are added (__dmul_rn: no FMA contraction): a neighbour on another GPU arrives as the
-  // already rounded product in the ghost array, and the sum must be bitwise the same either way
-  double v = __dmul_rn(G.spheremp[(size_t)e * 16 + n], f[i]);
-  const int* gs = G.gsrc + (size_t)e * NSLOT;
-  TSE_UNROLL
-  for (int t = 0; t < 3; ++t) {
-    const int slot = c_node_slots[n][t];
-    if (slot < 0) break;
-    const int s = gs[slot];
-    if (s == -1) continue;
-    if (s >= 0) {
-      const int es = s >> 4, nd = s & 15;
-      v += __dmul_rn(G.spheremp[(size_t)es * 16 + nd], f[lplane(es, k) * 16 + nd]);
-    } else {
-      v += ghost[(size_t)(-s - 2) * NLEV + k];
-    }
-  }
-  out[i] = v * G.rspheremp[(size_t)e * 16 + n];
-}
-
 // ---------------------------------------------------------------------------------------------
 // tracer-field kernels (one thread per (element, level, tracer) plane)
 // ---------------------------------------------------------------------------------------------

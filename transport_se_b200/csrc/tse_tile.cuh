@@ -440,6 +440,113 @@ __device__ __forceinline__ void laplace_wk_el(const double (&s)[16], const Dvv& 
   }
 }
 
+// DSS of one level field (the DSSopt variable of euler_step, prim_advection_mod.F90:913-919,943-958):
+// out = rspheremp * sum_{sharing elements} spheremp*f, in the reference's unpack order.  CTA = group, walking the 18 level chunks.
+// The group's 64 planes of a chunk (8 KB contiguous) are staged in shared memory as spheremp*f with coalesced loads, the nodes
+// of the group's perimeter that belong to other groups (the halo list of the tile kernels) or other GPUs (ghost_lev, already
+// weighted) next to them; a thread then sums the up to 3 contributions of each of its 4 nodes from shared memory.  Products are
+// rounded before they are added (__dmul_rn: no FMA contraction): a neighbour on another GPU arrives as the already rounded
+// product, and the sum must be bitwise the same either way.  (The node-per-thread version chased gather-table -> neighbour ->
+// value through global memory for 12 of 16 nodes: 1.0 ms per field at ne120, a quarter of the HBM rate.)
+__constant__ signed char c_node_slots_t[16][3] = {
+    {0, 12, 16}, {1, -1, -1}, {2, -1, -1},  {3, 4, 17},   // j = 0: S edge; node 0 also W and SW, node 3 also E and SE
+    {13, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {5, -1, -1},  // j = 1: W, interior, interior, E
+    {14, -1, -1}, {-1, -1, -1}, {-1, -1, -1}, {6, -1, -1},  // j = 2
+    {8, 15, 19}, {9, -1, -1}, {10, -1, -1}, {7, 11, 18}};  // j = 3: N edge; node 12 = N, W, NW; node 15 = E, N, NE
+constexpr int DSL_THREADS = GPL * 4;  // 4 threads per plane, 4 consecutive nodes (one row) each
+__host__ __device__ constexpr int dss_level_smem_bytes(int hmax) { return 2 * (GPL * 16 + hmax * KC) * 8; }
+
+__global__ void __launch_bounds__(DSL_THREADS) k_dss_level(Geo G, TileTables tb, const double* __restrict__ f, const double* __restrict__ ghost,
+                                                          double* __restrict__ out) {
+  extern __shared__ double dsm[];  // [buf 2][GPL*16 tile | hmax*KC halo]
+  const int t = threadIdx.x, g = blockIdx.x;
+  const int W = GPL * 16 + tb.hmax * KC;
+  const int hoff = tb.halo_off[g], H = tb.halo_off[g + 1] - hoff;
+  // loader role: 4 consecutive nodes of plane pl (coalesced 32-byte pieces); the halo entries (h, kk), level fastest
+  const int pl = t >> 2, r4 = (t & 3) * 4, el = pl / KC, kk = pl % KC;
+  const int e = min(g * GE + el, G.nelem - 1);
+  const double4 sp = *reinterpret_cast<const double4*>(G.spheremp + (size_t)e * 16 + r4);
+  const double4 rs = *reinterpret_cast<const double4*>(G.rspheremp + (size_t)e * 16 + r4);
+  constexpr int HI = 2;  // halo items per thread in registers (hmax*KC <= 2*DSL_THREADS = 512 covers hmax <= 128)
+  const double* h_src[HI];
+  double h_w[HI];
+  int h_stride[HI];
+  TSE_UNROLL
+  for (int i = 0; i < HI; ++i) {
+    const int it = t + i * DSL_THREADS;
+    h_src[i] = f; h_w[i] = 0.0; h_stride[i] = 0;
+    if (it < H * KC) {
+      const int h = it / KC, k2 = it % KC;
+      const int code = tb.halo_src[hoff + h];
+      if (code >= 0) {  // node (code & 15) of element (code >> 4): spheremp * f
+        const int es = code >> 4, nd = code & 15;
+        h_src[i] = f + lplane(es, k2) * 16 + nd;
+        h_w[i] = G.spheremp[(size_t)es * 16 + nd];
+        h_stride[i] = GPL * 16;  // doubles between level chunks of a level field
+      } else {          // ghost slot: already the rounded product, [slot][k]
+        h_src[i] = ghost + (size_t)(-code - 2) * NLEV + k2;
+        h_w[i] = -1.0;
+        h_stride[i] = KC;
+      }
+    }
+  }
+  // consumer role: the same 4 nodes; up to 3 contributions each, as offsets into a shared-memory buffer (-1: none)
+  short coff[4][3];
+  {
+    const int* gs = tb.gsrc_t + (size_t)e * NSLOT;
+    TSE_UNROLL
+    for (int j = 0; j < 4; ++j)
+      TSE_UNROLL
+      for (int c = 0; c < 3; ++c) {
+        const int slot = c_node_slots_t[r4 + j][c];
+        int off = -1;
+        if (slot >= 0) {
+          const int code = gs[slot];
+          if (code >= 256) off = GPL * 16 + (code - 256) * KC + kk;
+          else if (code >= 0) off = ((code >> 4) * KC + kk) * 16 + (code & 15);
+        }
+        coff[j][c] = (short)off;
+      }
+  }
+  const bool evalid = g * GE + el < G.nelem;
+  const size_t base = ((size_t)g * NKC * GPL + pl) * 16 + r4;  // (chunk 0, plane pl, node r4) of this group in a level field
+  double4 r_own;
+  double r_h[HI];
+  auto prefetch = [&](int kc) {
+    r_own = *reinterpret_cast<const double4*>(f + base + (size_t)kc * GPL * 16);
+    TSE_UNROLL
+    for (int i = 0; i < HI; ++i)
+      if (t + i * DSL_THREADS < H * KC) r_h[i] = h_src[i][(size_t)kc * h_stride[i]];
+  };
+  prefetch(0);
+  for (int kc = 0; kc < NKC; ++kc) {
+    double* sb = dsm + (size_t)(kc & 1) * W;
+    *reinterpret_cast<double4*>(sb + pl * 16 + r4) =
+        make_double4(__dmul_rn(sp.x, r_own.x), __dmul_rn(sp.y, r_own.y), __dmul_rn(sp.z, r_own.z), __dmul_rn(sp.w, r_own.w));
+    TSE_UNROLL
+    for (int i = 0; i < HI; ++i)
+      if (t + i * DSL_THREADS < H * KC) sb[GPL * 16 + t + i * DSL_THREADS] = h_w[i] < 0.0 ? r_h[i] : __dmul_rn(h_w[i], r_h[i]);
+    for (int it = t + HI * DSL_THREADS; it < H * KC; it += DSL_THREADS) {  // groups with more than 128 perimeter nodes
+      const int h = it / KC, k2 = it % KC;
+      const int code = tb.halo_src[hoff + h];
+      const int kq = kc * KC + k2;
+      sb[GPL * 16 + it] = code >= 0 ? __dmul_rn(G.spheremp[(size_t)(code >> 4) * 16 + (code & 15)], f[lplane(code >> 4, kq) * 16 + (code & 15)])
+                                    : ghost[(size_t)(-code - 2) * NLEV + kq];
+    }
+    __syncthreads();
+    if (kc + 1 < NKC) prefetch(kc + 1);
+    const double* own = sb + pl * 16 + r4;
+    double v[4] = {own[0], own[1], own[2], own[3]};
+    TSE_UNROLL
+    for (int j = 0; j < 4; ++j)
+      TSE_UNROLL
+      for (int c = 0; c < 3; ++c)
+        if (coff[j][c] >= 0) v[j] += sb[coff[j][c]];
+    if (evalid)
+      *reinterpret_cast<double4*>(out + base + (size_t)kc * GPL * 16) = make_double4(v[0] * rs.x, v[1] * rs.y, v[2] * rs.z, v[3] * rs.w);
+  }
+}
+
 // min/max over the element and its up to 8 neighbours (neighbor_minmax, viscosity_mod.F90:748-816).
 // CTA = (group, level chunk), walking the tracers two at a time.  The element extrema of the group (2 x 512 contiguous bytes per
 // tracer) and of the neighbour elements outside the group (one 32-byte sector each: the KC = 4 levels of a chunk are contiguous
