@@ -171,7 +171,6 @@ inline int edge_node(int d, int t) {
 inline int corner_node(int d) { return d == SWEST ? 0 : d == SEAST ? 3 : d == NWEST ? 12 : 15; }
 
 dim3 plane_grid(const tse_state* s) { return dim3((unsigned)(s->ngroups * NKC), (unsigned)((s->Q + QPB - 1) / QPB)); }
-unsigned level_blocks(const tse_state* s) { return (unsigned)(((size_t)s->ngroups * NKC * GPL + 127) / 128); }
 
 DssView view(const tse_state* s, int buf, int pending) {
   DssView v;
@@ -1023,7 +1022,7 @@ int tse_get_qminmax(tse_handle s, double* qmin, double* qmax) {
 int tse_precompute_divdp(tse_handle s) {
   if (!s) return fail("tse_precompute_divdp: null handle");
   if (poll_device_error(s)) return 1;
-  k_divdp<<<level_blocks(s), 128, 0, s->stream>>>(s->geo, s->dvv, s->vn0, s->divdp, s->divdp_proj);
+  k_divdp<<<s->ngroups * NKC / 2, DV_THREADS, DV_SMEM, s->stream>>>(s->geo, s->dvv, s->vn0, s->divdp, s->divdp_proj);
   ++s->launches;
   CU(cudaGetLastError());
   return 0;

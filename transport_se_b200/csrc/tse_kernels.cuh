@@ -90,26 +90,72 @@ __device__ __forceinline__ bool thread_level(const Geo& G, int& e, int& k) {
 }
 
 // divdp = divergence_sphere(vn0); divdp_proj = divdp   (prim_advection_mod.F90:614-623)
-__global__ void __launch_bounds__(128) k_divdp(Geo G, Dvv D, const double* __restrict__ vn0, double* __restrict__ divdp,
-                                               double* __restrict__ divdp_proj) {
-  int e, k;
-  if (!thread_level(G, e, k)) return;
-  double v1[16], v2[16], g1[16], g2[16], r[16];
-  load16(vn0 + vplane(e, k, 0) * 16, v1);
-  load16(vn0 + vplane(e, k, 1) * 16, v2);
-  const double* mD = G.mD + (size_t)e * 64;
+// One CTA per two level chunks of a group (NKC is even): the 32 KB of vn0 and the group's metric terms go through shared
+// memory with coalesced 16-byte accesses (rows padded to 144 bytes: a thread then reads its own 128-byte plane conflict-free),
+// and so do the 16 KB of results.  (One plane per thread straight from global memory ran at 2.5 TB/s.)
+constexpr int DV_THREADS = 2 * GPL, DV_ROW = 144, DV_MD = 64 * 8 + 16, DV_RM = 16 * 8 + 16;
+constexpr int DV_SMEM = 4 * GPL * DV_ROW + GE * DV_MD + GE * DV_RM;
+static_assert(NKC % 2 == 0, "k_divdp pairs level chunks");
+__global__ void __launch_bounds__(DV_THREADS) k_divdp(Geo G, Dvv D, const double* __restrict__ vn0, double* __restrict__ divdp,
+                                                      double* __restrict__ divdp_proj) {
+  extern __shared__ __align__(16) unsigned char dv_smem[];
+  unsigned char* const sv = dv_smem;                    // [chunk][component][plane] rows of vn0
+  unsigned char* const smd = sv + 4 * GPL * DV_ROW;     // [element][4][16] metric terms
+  unsigned char* const srm = smd + GE * DV_MD;          // [element][16] rmetdet
+  const int t = threadIdx.x;
+  const size_t c0 = (size_t)blockIdx.x * 2;             // first chunk: (g, kc) = (c0 / NKC, c0 % NKC)
+  const int g = (int)(c0 / NKC), kc0 = (int)(c0 % NKC);
+  {
+    const double2* src = reinterpret_cast<const double2*>(vn0 + c0 * 2 * GPL * 16);
+    TSE_UNROLL
+    for (int j = 0; j < 16; ++j) {
+      const int i = t + DV_THREADS * j;
+      *reinterpret_cast<double2*>(sv + (i >> 3) * DV_ROW + (i & 7) * 16) = src[i];
+    }
+    const int elast = G.nelem - 1;
+    for (int i = t; i < GE * 32; i += DV_THREADS) {
+      const int el = i >> 5, c = i & 31, e = min(g * GE + el, elast);
+      *reinterpret_cast<double2*>(smd + el * DV_MD + c * 16) = *reinterpret_cast<const double2*>(G.mD + (size_t)e * 64 + 2 * c);
+    }
+    if (t < GE * 8) {
+      const int el = t >> 3, c = t & 7, e = min(g * GE + el, elast);
+      *reinterpret_cast<double2*>(srm + el * DV_RM + c * 16) = *reinterpret_cast<const double2*>(G.rmr + (size_t)e * 16 + 2 * c);
+    }
+  }
+  __syncthreads();
+  const int cl = t / GPL, pl = t % GPL, el = pl / KC;
+  unsigned char* const row1 = sv + ((cl * 2) * GPL + pl) * DV_ROW;
+  const unsigned char* const row2 = row1 + GPL * DV_ROW;
+  double g1[16], g2[16], r[16];
   TSE_UNROLL
-  for (int n = 0; n < 16; ++n) {
-    g1[n] = mD[n] * v1[n] + mD[16 + n] * v2[n];
-    g2[n] = mD[32 + n] * v1[n] + mD[48 + n] * v2[n];
+  for (int c = 0; c < 8; ++c) {
+    const double2 a1 = *reinterpret_cast<const double2*>(row1 + c * 16), a2 = *reinterpret_cast<const double2*>(row2 + c * 16);
+    const unsigned char* m = smd + el * DV_MD + c * 16;
+    const double2 m11 = *reinterpret_cast<const double2*>(m), m12 = *reinterpret_cast<const double2*>(m + 128);
+    const double2 m21 = *reinterpret_cast<const double2*>(m + 256), m22 = *reinterpret_cast<const double2*>(m + 384);
+    g1[2 * c] = m11.x * a1.x + m12.x * a2.x;
+    g1[2 * c + 1] = m11.y * a1.y + m12.y * a2.y;
+    g2[2 * c] = m21.x * a1.x + m22.x * a2.x;
+    g2[2 * c + 1] = m21.y * a1.y + m22.y * a2.y;
   }
   div_contract(g1, g2, D, r);
-  const double* rmr = G.rmr + (size_t)e * 16;
   TSE_UNROLL
-  for (int n = 0; n < 16; ++n) r[n] = r[n] * rmr[n];
-  const size_t lp = lplane(e, k) * 16;
-  store16(divdp + lp, r);
-  store16(divdp_proj + lp, r);
+  for (int c = 0; c < 8; ++c) {
+    const double2 rm = *reinterpret_cast<const double2*>(srm + el * DV_RM + c * 16);
+    *reinterpret_cast<double2*>(row1 + c * 16) = make_double2(r[2 * c] * rm.x, r[2 * c + 1] * rm.y);  // (only this thread reads row1)
+  }
+  __syncthreads();
+  double2* const o1 = reinterpret_cast<double2*>(divdp + c0 * GPL * 16);
+  double2* const o2 = reinterpret_cast<double2*>(divdp_proj + c0 * GPL * 16);
+  TSE_UNROLL
+  for (int j = 0; j < 8; ++j) {
+    const int i = t + DV_THREADS * j, orow = i >> 3;
+    if (g * GE + (orow % GPL) / KC >= G.nelem) continue;  // padding elements of the last group
+    const double2 v = *reinterpret_cast<const double2*>(sv + ((orow / GPL) * 2 * GPL + orow % GPL) * DV_ROW + (i & 7) * 16);
+    o1[i] = v;
+    o2[i] = v;
+  }
+  (void)kc0;
 }
 
 // ---------------------------------------------------------------------------------------------
