@@ -428,7 +428,11 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
       S[2 * c] = v.x;
       S[2 * c + 1] = v.y;
     }
+#ifdef TSE_EXP_SKIP_GATHER  // timing experiment only: wrong results
+    if (false) {
+#else
     if (a.pending[which]) {  // DSS in the reference's unpack order: S, E, N, W edges, then SW, SE, NE, NW corners
+#endif
       TSE_UNROLL
       for (int i = 0; i < 4; ++i) S[i] += lds64(inb, gofs(i));
       TSE_UNROLL
@@ -535,7 +539,11 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
         TSE_UNROLL
         for (int n = 0; n < 16; ++n) keep[n] = cf * lap[n];
       } else if (kStage) {
+#ifdef TSE_EXP_SKIP_S2CHECK  // timing experiment only: wrong results
+        if (false) {
+#else
         if (OP == OP_STAGE2) {
+#endif
           // qmin = min(qmin, minval(Q)), qmax = max(qmax, maxval(Q)) with Q = rspheremp*DSS/dp (:779-792).  Away from tracer fronts
           // every Q already lies inside the bounds of stage 1: test that first (2 DSETP per node, no selects) and reduce only
           // where it fails -- the result is the same either way.
