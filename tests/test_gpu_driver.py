@@ -52,6 +52,32 @@ def test_device_driver_matches_oracle(built, test, qsize):
     adv.close()
 
 
+@pytest.mark.parametrize("ne,qsize,test", [(2, 1, 11), (3, 3, 12), (5, 7, 11)])
+def test_tiny_meshes_and_ragged_tiles(built, ne, qsize, test):
+    """Edge shapes of the tiling: a single tracer (half-empty pipeline item), odd tracer counts, meshes of 24 / 54 / 150
+    elements (1.5, 3.4 and 9.4 groups of 16: padded last group; at ne=2 every element touches a cube corner and a group's halo
+    comes mostly from itself), against the oracle over two remap cycles."""
+    from transport_se_b200.advection import TracerAdvection
+    tstep = 600.0
+    m, v, hv, o = make_oracle(ne, qsize, test, nu_q=1e17)
+    adv = TracerAdvection(m, v, hv, qsize=qsize, nu_q=1e17)
+    adv.dcmip_init(test)
+    got = np.zeros_like(o.Qdp)
+    nstep = 0
+    for cyc in range(2):
+        assert o.prim_run_subcycle(tstep) == 0
+        nstep = adv.prim_run_subcycle(tstep, nstep)
+        n0, _ = o.qdp_levels()
+        adv.copy_qdp_d2h(got, n0)
+        err = per_tracer_relerr(got[:, n0 - 1], o.Qdp[:, n0 - 1])
+        print("ne", ne, "qsize", qsize, "cycle", cyc, "relerr", err)
+        assert err.max() < 5e-12
+    mass = adv.diag_mass(n0)
+    ref = (o.Qdp[:, n0 - 1] * m.spheremp[:, None, None, :]).sum(axis=(0, 2, 3))
+    assert np.max(np.abs(mass - ref) / np.abs(ref)) < 1e-12
+    adv.close()
+
+
 def test_mass_is_order_independent(built):
     """The fixed-point mass sum must be bitwise identical whatever the internal element order (with / without SFC sort)."""
     from transport_se_b200.advection import TracerAdvection
