@@ -288,13 +288,32 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
   // With 2 CTAs per SM the consumer warps of a starting CTA otherwise sit out ~25 % of the CTA's lifetime here.
   const bool main_pending = kS3 ? (a.pending[1] != 0) : (a.pending[0] != 0);
   const int elast = G.nelem - 1;
+  // The stage ops need 11 double2 per (plane, chunk) pair, 6 of them geometry of the element (spheremp, rspheremp, the metric):
+  // the group's geometry (12 KB) goes through the OUT tile, which nothing uses before the first item is done, as 16-byte cp.async
+  // -- 6 per thread, no registers -- and the 5 level fields of all NPK pairs are loaded at once: one HBM round trip for the
+  // whole prologue (with everything in registers it took two batches, i.e. two dependent round trips).
+  constexpr bool kGeoStage = kStage && TT == GE * 8 && GPL * 8 == 4 * TT;
+  constexpr int GS_SP = 0, GS_RS = GE * 128, GS_MD = 2 * GE * 128;  // [el][16], [el][16], [el][4][16] doubles from outb
+  if (kGeoStage) {
+    const unsigned ob32 = smem_u32 + (unsigned)(outb - smem);
+    const int ee = min(g * GE + (t >> 3), elast), c = t & 7;
+    cp_async16(ob32 + GS_SP + t * 16, G.spheremp + (size_t)ee * 16 + 2 * c);
+    cp_async16(ob32 + GS_RS + t * 16, G.rspheremp + (size_t)ee * 16 + 2 * c);
+    TSE_UNROLL
+    for (int j = 0; j < 4; ++j) {
+      const int id = t + TT * j, em = min(g * GE + (id >> 5), elast);
+      cp_async16(ob32 + GS_MD + id * 16, G.mD + (size_t)em * 64 + 2 * (id & 31));
+    }
+  }
   double2 L_sp = make_double2(0, 0), L_rs = L_sp, L_rm = L_sp, L_t11 = L_sp, L_t12 = L_sp, L_t22 = L_sp;
   const bool el_thread = cfg.nel > 0 && t < GE * 8;
   if (el_thread) {
     const int c = t & 7, ee = min(g * GE + (t >> 3), elast);
     const size_t b = (size_t)ee * 16 + 2 * c;
-    L_sp = *reinterpret_cast<const double2*>(G.spheremp + b);
-    L_rs = *reinterpret_cast<const double2*>(G.rspheremp + b);
+    if (!kGeoStage) {
+      L_sp = *reinterpret_cast<const double2*>(G.spheremp + b);
+      L_rs = *reinterpret_cast<const double2*>(G.rspheremp + b);
+    }
     L_rm = *reinterpret_cast<const double2*>(G.rmr + b);
     if (cfg.T11 >= 0) {
       const double* T = G.T + (size_t)ee * 48 + 2 * c;
@@ -303,25 +322,32 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
       L_t22 = *reinterpret_cast<const double2*>(T + 32);
     }
   }
-  // (plane, 16-byte chunk) pairs of the GPL x 8 chunks, strided over the consumer threads; loads are issued for PB pairs at a
-  // time (all NPK at once would need more registers than the kernel has)
-  constexpr int NPK = (GPL * 8) / TT, PB = NPK % 2 == 0 ? 2 : 1;
+  // (plane, 16-byte chunk) pairs of the GPL x 8 chunks, strided over the consumer threads; the loads of PB pairs are issued
+  // before the first of them is used
+  constexpr int NPK = (GPL * 8) / TT, PB = (kGeoStage || !kStage) ? NPK : (NPK % 2 == 0 ? 2 : 1);
   static_assert((GPL * 8) % TT == 0, "package pairs divide evenly over the consumer threads");
-  if (el_thread) {
-    const int pe = t >> 3, c = t & 7;
-    const double rx0 = main_pending ? L_rs.x : 1.0, rx1 = main_pending ? L_rs.y : 1.0;
-    const double2 e1 = OP == OP_MASS ? L_sp : make_double2(L_sp.x * rx0, L_sp.y * rx1);
-    const double2 e2 = make_double2(a.dt * (L_sp.x * L_rm.x), a.dt * (L_sp.y * L_rm.y));
-    const int off = (c * GE + pe) * 16;
-    if (cfg.E1 >= 0) *reinterpret_cast<double2*>(elb + cfg.E1 * EL_BYTES + off) = e1;
-    if (cfg.E2 >= 0) *reinterpret_cast<double2*>(elb + cfg.E2 * EL_BYTES + off) = e2;
-    if (cfg.RSPH >= 0) *reinterpret_cast<double2*>(elb + cfg.RSPH * EL_BYTES + off) = L_rs;
-    if (cfg.T11 >= 0) {
-      *reinterpret_cast<double2*>(elb + cfg.T11 * EL_BYTES + off) = L_t11;
-      *reinterpret_cast<double2*>(elb + cfg.T12 * EL_BYTES + off) = L_t12;
-      *reinterpret_cast<double2*>(elb + cfg.T22 * EL_BYTES + off) = L_t22;
+  auto store_el = [&]() {
+    if (el_thread) {
+      const int pe = t >> 3, c = t & 7;
+      if (kGeoStage) {
+        L_sp = lds128(outb, GS_SP + t * 16);
+        L_rs = lds128(outb, GS_RS + t * 16);
+      }
+      const double rx0 = main_pending ? L_rs.x : 1.0, rx1 = main_pending ? L_rs.y : 1.0;
+      const double2 e1 = OP == OP_MASS ? L_sp : make_double2(L_sp.x * rx0, L_sp.y * rx1);
+      const double2 e2 = make_double2(a.dt * (L_sp.x * L_rm.x), a.dt * (L_sp.y * L_rm.y));
+      const int off = (c * GE + pe) * 16;
+      if (cfg.E1 >= 0) *reinterpret_cast<double2*>(elb + cfg.E1 * EL_BYTES + off) = e1;
+      if (cfg.E2 >= 0) *reinterpret_cast<double2*>(elb + cfg.E2 * EL_BYTES + off) = e2;
+      if (cfg.RSPH >= 0) *reinterpret_cast<double2*>(elb + cfg.RSPH * EL_BYTES + off) = L_rs;
+      if (cfg.T11 >= 0) {
+        *reinterpret_cast<double2*>(elb + cfg.T11 * EL_BYTES + off) = L_t11;
+        *reinterpret_cast<double2*>(elb + cfg.T12 * EL_BYTES + off) = L_t12;
+        *reinterpret_cast<double2*>(elb + cfg.T22 * EL_BYTES + off) = L_t22;
+      }
     }
-  }
+  };
+  if (cfg.npp == 0) store_el();
   if (cfg.npp > 0) {
     TSE_UNROLL
     for (int r0b = 0; r0b < NPK; r0b += PB) {
@@ -334,23 +360,42 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
         const size_t lp = lplane(pe, pk) * 16 + n, gb = (size_t)pe * 16 + n;
         P_dp[r] = *reinterpret_cast<const double2*>(a.dp + lp);
         P_dj[r] = *reinterpret_cast<const double2*>(a.divdp_proj + lp);
-        P_rs[r] = *reinterpret_cast<const double2*>(G.rspheremp + gb);
+        if (!kGeoStage) P_rs[r] = *reinterpret_cast<const double2*>(G.rspheremp + gb);
         if (kStage) {
           P_dd[r] = *reinterpret_cast<const double2*>(a.divdp + lp);
           P_v1[r] = *reinterpret_cast<const double2*>(a.vn0 + vplane(pe, pk, 0) * 16 + n);
           P_v2[r] = *reinterpret_cast<const double2*>(a.vn0 + vplane(pe, pk, 1) * 16 + n);
-          P_sp[r] = *reinterpret_cast<const double2*>(G.spheremp + gb);
-          const double* mD = G.mD + (size_t)pe * 64 + n;
-          P_m11[r] = *reinterpret_cast<const double2*>(mD);
-          P_m12[r] = *reinterpret_cast<const double2*>(mD + 16);
-          P_m21[r] = *reinterpret_cast<const double2*>(mD + 32);
-          P_m22[r] = *reinterpret_cast<const double2*>(mD + 48);
+          if (!kGeoStage) {
+            P_sp[r] = *reinterpret_cast<const double2*>(G.spheremp + gb);
+            const double* mD = G.mD + (size_t)pe * 64 + n;
+            P_m11[r] = *reinterpret_cast<const double2*>(mD);
+            P_m12[r] = *reinterpret_cast<const double2*>(mD + 16);
+            P_m21[r] = *reinterpret_cast<const double2*>(mD + 32);
+            P_m22[r] = *reinterpret_cast<const double2*>(mD + 48);
+          }
         }
+      }
+      if (r0b == 0) {
+        if (kGeoStage) {
+          cp_async_wait_all();
+          consumer_barrier();  // every thread's part of the geometry has landed
+        }
+        store_el();
       }
       TSE_UNROLL
       for (int r = 0; r < PB; ++r) {
         const int i = t + (r0b + r) * TT;
         const int ppl = i >> 3, c = i & 7;
+        if (kGeoStage) {
+          const int ge = (ppl / KC) * 128 + c * 16;
+          P_sp[r] = lds128(outb, GS_SP + ge);
+          P_rs[r] = lds128(outb, GS_RS + ge);
+          const int gm = GS_MD + (ppl / KC) * 512 + c * 16;
+          P_m11[r] = lds128(outb, gm);
+          P_m12[r] = lds128(outb, gm + 128);
+          P_m21[r] = lds128(outb, gm + 256);
+          P_m22[r] = lds128(outb, gm + 384);
+        }
         double2 u1 = make_double2(0, 0), u2 = u1, cl = make_double2(1, 1), rcl = make_double2(1, 1);
         const double rx0 = main_pending ? P_rs[r].x : 1.0, rx1 = main_pending ? P_rs[r].y : 1.0;
         const double dps0 = P_dp[r].x - a.rhs_mult_dt * P_dj[r].x, dps1 = P_dp[r].y - a.rhs_mult_dt * P_dj[r].y;
@@ -644,7 +689,7 @@ __global__ void __launch_bounds__(pipe_threads(OP), (pipe_threads(OP) > 256 ? 1 
       }
     }
   }
-  if (kHasOut && lane == 0) bulk_wait0();
+  if (kHasOut && lane == 0) bulk_wait0();  // (waiting for the reads only, wait_group.read, measured the same)
 
 }
 

@@ -107,6 +107,11 @@ __device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src));
 }
 
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 __device__ __forceinline__ double2 lds128(const unsigned char* base, int off) { return *reinterpret_cast<const double2*>(base + off); }
 __device__ __forceinline__ double lds64(const unsigned char* base, int off) { return *reinterpret_cast<const double*>(base + off); }
 
