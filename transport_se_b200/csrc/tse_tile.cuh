@@ -569,7 +569,10 @@ struct NbrTables {
   const int* ext_src;  // [ext_off[ngroups]]: >= 0 element (internal order), <= -2 ghost bundle -(v + 2)
   int xmax;            // max external entries of a group
 };
-constexpr int NBQ = 2;  // tracers per batch = NBQ * GPL threads
+#ifndef TSE_NBQ
+#define TSE_NBQ 2
+#endif
+constexpr int NBQ = TSE_NBQ;  // tracers per batch = NBQ * GPL threads
 __host__ __device__ constexpr int nbr_smem_bytes(int xmax) { return 2 * 2 * NBQ * (GPL + xmax * KC) * 8; }
 static_assert(KC == 4 && NLEV % KC == 0, "k_nbr_minmax moves the 4 levels of a chunk as two double2");
 
