@@ -1374,6 +1374,17 @@ int tse_diag_qminmax(tse_handle s, int tl, double* qmin, double* qmax) {
   return check_device_error(s);
 }
 
+#ifdef TSE_EXP_LIMSTATS
+extern "C" int tse_exp_limiter_stats(unsigned long long* out4, int reset) {
+  cudaDeviceSynchronize();
+  if (out4 && cudaMemcpyFromSymbol(out4, tse::g_lim_stats, 32) != cudaSuccess) return 1;
+  if (reset) {
+    const unsigned long long z[4] = {0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(tse::g_lim_stats, z, 32) != cudaSuccess) return 1;
+  }
+  return 0;
+}
+#endif
 int tse_debug_limiter(int n, double* ptens_w, const double* sphweights, const double* dpmass, double* minp, double* maxp) {
   if (n <= 0) return 0;
   if (!ptens_w || !sphweights || !dpmass || !minp || !maxp) return fail("tse_debug_limiter: null argument");

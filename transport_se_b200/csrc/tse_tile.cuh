@@ -218,6 +218,9 @@ __device__ __forceinline__ unsigned limiter_check(const double (&y)[16], unsigne
   return any_outside(x, minp, maxp);
 }
 
+#ifdef TSE_EXP_LIMSTATS
+__device__ unsigned long long g_lim_stats[4];
+#endif
 // limiter_slow: the clip / redistribute sweeps, for a plane limiter_check flagged (minp/maxp already relaxed, mass from the check).
 __device__ __forceinline__ void limiter_slow(double (&y)[16], unsigned cbase, unsigned rcbase, double mass, double minp, double maxp) {
   const double tol_limiter = (double)5e-14f;
@@ -327,7 +330,21 @@ __device__ __forceinline__ void limiter_slow(double (&y)[16], unsigned cbase, un
 __device__ __forceinline__ void limiter_y(double (&y)[16], unsigned cbase, unsigned rcbase, double sumc, double& minp, double& maxp) {
   if (sumc <= 0.0) return;  // (:1016)
   double mass;
-#ifdef TSE_EXP_SKIP_SLOW  // timing experiment only: wrong results (the check runs, the sweeps do not)
+#ifdef TSE_EXP_LIMSTATS  // counting experiment: warps that reach the limiter / that enter the sweeps / lanes active in them
+  {
+    const bool need = limiter_check(y, rcbase, sumc, minp, maxp, mass);
+    const unsigned act = __activemask(), bal = __ballot_sync(act, need);
+    if ((threadIdx.x & 31) == (__ffs(act) - 1)) {
+      atomicAdd(&g_lim_stats[0], 1ull);
+      atomicAdd(&g_lim_stats[1], (unsigned long long)__popc(act));
+      if (bal) {
+        atomicAdd(&g_lim_stats[2], 1ull);
+        atomicAdd(&g_lim_stats[3], (unsigned long long)__popc(bal));
+      }
+    }
+    if (need) limiter_slow(y, cbase, rcbase, mass, minp, maxp);
+  }
+#elif defined(TSE_EXP_SKIP_SLOW)  // timing experiment only: wrong results (the check runs, the sweeps do not)
   if (limiter_check(y, rcbase, sumc, minp, maxp, mass)) y[0] += 1e-300 * mass;
 #else
   if (limiter_check(y, rcbase, sumc, minp, maxp, mass)) limiter_slow(y, cbase, rcbase, mass, minp, maxp);
